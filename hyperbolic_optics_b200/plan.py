@@ -1,0 +1,231 @@
+"""Stack planner: payload -> flat tables the kernels consume.
+
+This is the host half of the hot path.  It does the O(A + B + F) work of the reference's
+``Structure.get_layers`` (``structure.py:195-233``) and layer constructors
+(``layers.py:265-308, 318-351, 450-460, 484-523, 637-666``) and leaves every O(A*B*F*T)
+step to the device:
+
+* ``kx[A] = sqrt(eps_prism) sin(theta)`` and ``k0[F] = 2 pi f``  (``structure.py:183-189``)
+* prism row scalings ``1/cos(theta)``, ``1/(n cos(theta))`` with ``theta = arcsin(kx/n)`` so the
+  grazing end points round exactly like the reference (``layers.py:91, 109-152``)
+* isotropic exit ``cos(theta_f)[A]`` (complex) and ``N`` (``layers.py:190-238, 641-643``)
+* per crystal layer: eps(f), mu(f) packed symmetric tensors, pre-rotated by the
+  *batch-independent* part ``Ry(phi + 1e-8) Rx(theta)`` of the Euler rotation
+  (``layers.py:26-66, 283``); the batch-dependent ``Rz(beta)`` is applied per point on the
+  device from ``cos(beta)[B]``, ``sin(beta)[B]`` tables, ``beta = azimuth + rotZ + 1e-9`` for
+  "relative", ``rotZ + 1e-9`` for "static"/Incident (``layers.py:284, 318-351``)
+* thickness in cm (``layers.py:301-308``), scalar or the swept ``[T]`` axis.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .materials import create_material, pack_symmetric, unpack_symmetric
+from .scenario import ScenarioSetup
+
+KIND_ISO_FILM = 1
+KIND_ANISO_FILM = 2
+KIND_ANISO_EXIT = 3
+KIND_ISO_EXIT = 4
+
+TYPE_PRISM = "Ambient Incident Layer"
+TYPE_ISO_FILM = "Isotropic Middle-Stack Layer"
+TYPE_CRYSTAL = "Crystal Layer"
+TYPE_CRYSTAL_EXIT = "Semi Infinite Anisotropic Layer"
+TYPE_ISO_EXIT = "Semi Infinite Isotropic Layer"
+LAYER_TYPES = (TYPE_PRISM, TYPE_ISO_FILM, TYPE_CRYSTAL, TYPE_CRYSTAL_EXIT, TYPE_ISO_EXIT)
+
+
+@dataclass
+class LayerPlan:
+    kind: int
+    type: str
+    eps: np.ndarray | None = None      # [Fe, 6] complex128, Fe in {1, F}
+    mu: np.ndarray | None = None       # [Fm, 6] complex128, Fm in {1, F}
+    mu_scalar: bool = True             # mu proportional to identity (rotation-invariant)
+    cos_beta: np.ndarray | None = None  # [Bb] float64, Bb in {1, B}
+    sin_beta: np.ndarray | None = None
+    thickness: np.ndarray | None = None  # [Tt] float64 cm, Tt in {1, T}
+    iso_eps: complex = 1.0 + 0j
+    iso_mu: complex = 1.0 + 0j
+    exit_cos: np.ndarray | None = None   # [A] complex128
+    exit_n: float = 1.0
+    eps_exit: float | None = None
+    material: object = None
+
+
+@dataclass
+class StackPlan:
+    scenario: str
+    A: int
+    B: int
+    F: int
+    T: int
+    kx: np.ndarray
+    k0: np.ndarray
+    prism_inv_cos: np.ndarray
+    prism_inv_ncos: np.ndarray
+    prism_inv_n: float
+    layers: list = field(default_factory=list)
+    incident_angle: object = None
+    azimuthal_angle: object = None
+    frequency: np.ndarray | None = None
+    eps_prism: float | None = None
+
+    @property
+    def n_points(self):
+        return self.A * self.B * self.F * self.T
+
+    @property
+    def fabt_shape(self):
+        return (self.F, self.A, self.B, self.T)
+
+
+def _complex_scalar(value, default):
+    if value is None:
+        value = default
+    if isinstance(value, dict):
+        if "real" in value or "imag" in value:
+            return complex(value.get("real", 0), value.get("imag", 0))
+        raise ValueError("isotropic layer permittivity/permeability must be a scalar or {real, imag}")
+    return complex(value, 0)
+
+
+def validate_thickness_sweep(layer_data_list):
+    """At most one list-valued thickness (reference ``structure.py:235-257``)."""
+    swept = [i for i, layer in enumerate(layer_data_list)
+             if layer.get("thickness") is not None and not np.isscalar(layer.get("thickness"))]
+    if len(swept) > 1:
+        raise ValueError(
+            "Only one layer may have a list-valued 'thickness' (the canonical T axis); "
+            f"got swept layers at indices {swept}.")
+    return swept
+
+
+def resolve_frequency(explicit, layer_data_list):
+    """Explicit scalar/list wins, else the last material-bearing layer's default grid
+    (reference ``structure.py:142-170``)."""
+    if explicit is not None:
+        return np.atleast_1d(np.asarray(explicit, dtype=np.float64))
+    for layer in reversed(layer_data_list):
+        material = layer.get("material")
+        if material is not None:
+            freq = create_material(material).frequency
+            if freq is not None:
+                return np.asarray(freq, dtype=np.float64)
+    raise ValueError("No frequency given and no dispersive material to derive a range from; "
+                     "set ScenarioData['frequency'].")
+
+
+def _rotation_xy(theta_x, theta_y):
+    ct, st, cp, sp = math.cos(theta_x), math.sin(theta_x), math.cos(theta_y), math.sin(theta_y)
+    rx = np.array([[1.0, 0.0, 0.0], [0.0, ct, -st], [0.0, st, ct]])
+    ry = np.array([[cp, 0.0, sp], [0.0, 1.0, 0.0], [-sp, 0.0, cp]])
+    return ry @ rx
+
+
+def _beta_table(scenario, mode, rot_z, azimuth):
+    """cos/sin of the z rotation per azimuth sample; one entry when it does not vary."""
+    if scenario.type in ("Dispersion", "Azimuthal", "Simple", "FullSweep") and mode == "relative":
+        beta = np.atleast_1d(np.asarray(azimuth, dtype=np.float64) + rot_z)
+    else:
+        beta = np.atleast_1d(np.float64(rot_z))
+    return np.cos(beta), np.sin(beta)
+
+
+def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
+    if not layer_data_list or layer_data_list[0].get("type") != TYPE_PRISM:
+        kind = layer_data_list[0].get("type") if layer_data_list else None
+        if kind not in LAYER_TYPES:
+            raise ValueError(f"Invalid layer type {kind}")
+        raise ValueError("first layer must be the 'Ambient Incident Layer' (prism)")
+    validate_thickness_sweep(layer_data_list)
+    frequency = resolve_frequency(scenario.frequency, layer_data_list)
+    scenario.frequency = frequency
+
+    eps_prism = layer_data_list[0].get("permittivity", None)
+    inc = np.asarray(scenario.incident_angle, dtype=np.float64)
+    kx = np.atleast_1d(np.sqrt(np.float64(eps_prism)) * np.sin(inc)).astype(np.float64)
+    k0 = np.atleast_1d(frequency) * 2.0 * math.pi
+    az = scenario.azimuthal_angle
+    A, F = kx.size, k0.size
+    B = 1 if az is None or np.ndim(az) == 0 else int(np.size(az))
+
+    # prism: reference builds theta = arcsin(kx / n) and uses cos(theta) (layers.py:91,110)
+    eps_p = np.float64(layer_data_list[0].get("permittivity", 5.5))
+    n_p = np.sqrt(eps_p)
+    theta = np.arcsin(kx / np.sqrt(eps_p)).astype(np.float64)
+    cos_t = np.cos(theta)
+    with np.errstate(divide="ignore"):
+        inv_cos = 1.0 / cos_t
+        inv_ncos = 1.0 / (n_p * cos_t)
+
+    plan = StackPlan(scenario=scenario.type, A=A, B=B, F=F, T=1, kx=kx, k0=k0,
+                     prism_inv_cos=inv_cos, prism_inv_ncos=inv_ncos, prism_inv_n=float(1.0 / n_p),
+                     incident_angle=scenario.incident_angle, azimuthal_angle=az,
+                     frequency=frequency, eps_prism=eps_prism)
+
+    n_layers = len(layer_data_list)
+    for index, data in enumerate(layer_data_list[1:], start=1):
+        kind = data.get("type")
+        if kind not in LAYER_TYPES:
+            raise ValueError(f"Invalid layer type {kind}")
+        thickness = data.get("thickness", None)
+        if thickness is not None:
+            if np.isscalar(thickness):
+                thickness = np.array([float(thickness) * 1e-4])
+            else:
+                thickness = np.asarray(thickness, dtype=np.float64).reshape(-1) * 1e-4
+                plan.T = thickness.size
+        last = index == n_layers - 1
+
+        if kind == TYPE_ISO_FILM:
+            if thickness is None:
+                raise ValueError("Isotropic Middle-Stack Layer needs a thickness")
+            lp = LayerPlan(KIND_ISO_FILM, kind, thickness=thickness,
+                           iso_eps=_complex_scalar(data.get("permittivity", 1.0), 1.0),
+                           iso_mu=_complex_scalar(data.get("permeability", 1.0), 1.0))
+        elif kind in (TYPE_CRYSTAL, TYPE_CRYSTAL_EXIT):
+            material = create_material(data.get("material"))
+            theta_x = np.float64(math.radians(data.get("rotationX", 0)))
+            theta_y = np.float64(math.radians(data.get("rotationY", 0))) + 1e-8
+            rot_z = np.float64(math.radians(data.get("rotationZ", 0))) + 1.0e-9
+            mode = data.get("rotationZType", "relative")
+            q = _rotation_xy(theta_x, theta_y)
+            eps = pack_symmetric(q @ unpack_symmetric(material.eps_packed(frequency)) @ q.T)
+            mu_packed = material.mu_packed(frequency)
+            mu_scalar = bool(np.all(mu_packed[:, [1, 2, 4]] == 0)
+                             and np.all(mu_packed[:, 0] == mu_packed[:, 3])
+                             and np.all(mu_packed[:, 0] == mu_packed[:, 5]))
+            mu = mu_packed if mu_scalar else pack_symmetric(q @ unpack_symmetric(mu_packed) @ q.T)
+            cos_b, sin_b = _beta_table(scenario, mode, rot_z, az)
+            if kind == TYPE_CRYSTAL:
+                if thickness is None:
+                    raise ValueError("Crystal Layer needs a thickness")
+                lp = LayerPlan(KIND_ANISO_FILM, kind, thickness=thickness)
+            else:
+                lp = LayerPlan(KIND_ANISO_EXIT, kind)
+            lp.eps, lp.mu, lp.mu_scalar = np.ascontiguousarray(eps), np.ascontiguousarray(mu), mu_scalar
+            lp.cos_beta, lp.sin_beta, lp.material = cos_b, sin_b, material
+        elif kind == TYPE_ISO_EXIT:
+            eps_exit = data.get("permittivity")
+            if eps_exit is None:
+                raise ValueError("No exit permittivity provided for isotropic semi-infinite layer")
+            inc_flat = np.atleast_1d(inc).reshape(-1)
+            eps_incident = float((kx[0] / np.sin(inc_flat[0])) ** 2)
+            n_exit, n_inc = np.sqrt(np.float64(eps_exit)), np.sqrt(eps_incident)
+            inside = 1.0 - ((n_inc / n_exit) * np.sin(inc_flat)) ** 2.0
+            lp = LayerPlan(KIND_ISO_EXIT, kind, exit_cos=np.sqrt(inside.astype(np.complex128)),
+                           exit_n=float(n_exit), eps_exit=float(eps_exit))
+        elif kind == TYPE_PRISM:
+            raise ValueError("'Ambient Incident Layer' is only valid as the first layer")
+        if lp.kind in (KIND_ANISO_EXIT, KIND_ISO_EXIT) and not last:
+            raise ValueError(f"'{kind}' must be the last layer of the stack")
+        plan.layers.append(lp)
+    if not plan.layers or plan.layers[-1].kind not in (KIND_ANISO_EXIT, KIND_ISO_EXIT):
+        raise ValueError("the stack must end with a semi-infinite exit layer")
+    return plan

@@ -1,0 +1,484 @@
+"""NumPy model of the DEVICE algorithm (development + CPU-side algorithm tests).
+
+This is a vectorised, statement-for-statement model of what the CUDA kernels in
+``hyperbolic_optics_b200/csrc`` compute per point.  It exists so the eigenvector-free
+algorithm can be checked against the oracle on full grids in
+the CPU container.  It is NOT the oracle (that is ``oracle/reference_port.py``, a
+restatement of the reference's eig-based algorithm) and NOT a product path: nothing in
+``hyperbolic_optics_b200`` imports it.
+
+Per anisotropic layer (symmetric eps, mu rotated about z by beta):
+  1. Berreman matrix in its 9-parameter structured form
+        [[a, b, c, d], [0, e, f, -c], [g, h, e, -b], [j, -g, 0, a]]
+  2. characteristic quartic, Ferrari/Cardano roots, forward/backward classification,
+     Bairstow polish of the forward quadratic factor q_f; q_b by deflation
+  3. spectral projector P_f = q_b(D) h(D), h linear with h q_b = 1 (mod q_f)
+  4. substrate: forward plane = P_f [e0 e1];  film: exp(cD) Y = G_f P_f Y + G_b P_b Y with
+     2x2-block exponentials written in (mean, half-difference^2) of each root pair.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+IM_TOL = 1e-9  # reference waves.py:273
+
+
+# ----------------------------------------------------------------------------- tensors
+def rotate_z(t, cb, sb):
+    """Rz(beta) T Rz(beta)^T for symmetric T = (xx, xy, xz, yy, yz, zz)."""
+    xx, xy, xz, yy, yz, zz = t
+    c2, s2, cs = cb * cb, sb * sb, cb * sb
+    return (c2 * xx - 2.0 * cs * xy + s2 * yy,
+            cs * (xx - yy) + (c2 - s2) * xy,
+            cb * xz - sb * yz,
+            s2 * xx + 2.0 * cs * xy + c2 * yy,
+            sb * xz + cb * yz,
+            zz)
+
+
+def berreman9(k, e, m):
+    """Structured Berreman entries (a,b,c,d,e,f,g,h,j) -- reference waves.py:221-245 with
+    symmetric tensors."""
+    exx, exy, exz, eyy, eyz, ezz = e
+    mxx, mxy, mxz, myy, myz, mzz = m
+    ie, im = 1.0 / ezz, 1.0 / mzz
+    k2 = k * k
+    a = -k * exz * ie
+    b = k * (myz * im - eyz * ie)
+    c = mxy - myz * mxz * im
+    d = myy - myz * myz * im - k2 * ie
+    ee = -k * mxz * im
+    f = mxz * mxz * im - mxx
+    g = eyz * exz * ie - exy
+    h = k2 * im - eyy + eyz * eyz * ie
+    j = exx - exz * exz * ie
+    return a, b, c, d, ee, f, g, h, j
+
+
+def matvec(D, v):
+    """Structured D @ v for v = (v0, v1, v2, v3)."""
+    a, b, c, d, e, f, g, h, j = D
+    v0, v1, v2, v3 = v
+    return (a * v0 + b * v1 + c * v2 + d * v3,
+            e * v1 + f * v2 - c * v3,
+            g * v0 + h * v1 + e * v2 - b * v3,
+            j * v0 - g * v1 + a * v3)
+
+
+def charpoly(D):
+    """lambda^4 + c3 lambda^3 + c2 lambda^2 + c1 lambda + c0 = det(lambda I - D)."""
+    a, b, c, d, e, f, g, h, j = D
+    a2, e2, cg, dj, fh = a * a, e * e, c * g, d * j, f * h
+    bcj, bf = b * c * j, b * f
+    c3 = -2.0 * (a + e)
+    c2 = a2 + 4.0 * a * e - 2.0 * cg - dj + e2 - fh
+    c1 = -2.0 * (a2 * e - a * cg + a * e2 - a * fh - bcj + bf * g - e * cg - e * dj)
+    c0 = (a2 * e2 - a2 * fh + 2.0 * a * bf * g - 2.0 * a * e * cg + b * bf * j - 2.0 * e * bcj
+          + cg * cg + c * c * h * j - e2 * dj + d * f * g * g + dj * fh)
+    return c3, c2, c1, c0
+
+
+# ----------------------------------------------------------------------------- quartic
+_OMEGA = np.exp(2j * np.pi / 3.0)
+
+
+def _ccbrt(z):
+    r = np.abs(z)
+    th = np.angle(z)
+    return np.cbrt(r) * np.exp(1j * th / 3.0)
+
+
+def _quad_roots(bq, cq):
+    """Roots of y^2 + bq y + cq (cancellation-free)."""
+    sq = np.sqrt(bq * bq - 4.0 * cq)
+    sgn = np.where((np.conj(bq) * sq).real >= 0.0, 1.0, -1.0)
+    t = -0.5 * (bq + sgn * sq)
+    safe = np.abs(t) > 0.0
+    y2 = np.where(safe, cq / np.where(safe, t, 1.0), 0.0)
+    return t, y2
+
+
+def ferrari(c3, c2, c1, c0):
+    """Closed-form roots (start values only; polished later)."""
+    c3 = c3.astype(np.complex128)
+    q3 = 0.25 * c3
+    p = c2 - 6.0 * q3 * q3
+    q = c1 - 2.0 * q3 * c2 + 8.0 * q3 * q3 * q3
+    r = c0 - q3 * c1 + q3 * q3 * c2 - 3.0 * q3 ** 4
+    # resolvent m^3 + p m^2 + (p^2/4 - r) m - q^2/8 = 0 ; m = t - p/3
+    P = -p * p / 12.0 - r
+    Q = -p * p * p / 108.0 + p * r / 3.0 - q * q / 8.0
+    sq = np.sqrt(Q * Q / 4.0 + P * P * P / 27.0)
+    u3a, u3b = -Q / 2.0 + sq, -Q / 2.0 - sq
+    u3 = np.where(np.abs(u3a) >= np.abs(u3b), u3a, u3b)
+    u = _ccbrt(u3)
+    best_m, best_abs = None, None
+    for kk in range(3):
+        uk = u * _OMEGA ** kk
+        ok = np.abs(uk) > 0.0
+        tk = uk - np.where(ok, P / (3.0 * np.where(ok, uk, 1.0)), 0.0)
+        mk = tk - p / 3.0
+        ak = np.abs(mk)
+        if best_m is None:
+            best_m, best_abs = mk, ak
+        else:
+            take = ak > best_abs
+            best_m = np.where(take, mk, best_m)
+            best_abs = np.where(take, ak, best_abs)
+    m = best_m
+    alpha = np.sqrt(2.0 * m)
+    ok = np.abs(alpha) > 0.0
+    qa = np.where(ok, q / (2.0 * np.where(ok, alpha, 1.0)), 0.0)
+    beta1 = 0.5 * p + m - qa
+    beta2 = 0.5 * p + m + qa
+    y0, y1 = _quad_roots(alpha, beta1)
+    y2, y3 = _quad_roots(-alpha, beta2)
+    return [y - q3 for y in (y0, y1, y2, y3)]
+
+
+def newton_polish(roots, c3, c2, c1, c0, iters=2):
+    out = []
+    for lam in roots:
+        for _ in range(iters):
+            pv = (((lam + c3) * lam + c2) * lam + c1) * lam + c0
+            dv = ((4.0 * lam + 3.0 * c3) * lam + 2.0 * c2) * lam + c1
+            ok = np.abs(dv) > 1e-300
+            step = np.where(ok, pv / np.where(ok, dv, 1.0), 0.0)
+            # guard against wild steps at near-multiple roots
+            big = np.abs(step) > 0.5 * (np.abs(lam) + 1e-300)
+            lam = lam - np.where(big, 0.0, step)
+        out.append(lam)
+    return out
+
+
+def classify_forward(roots):
+    """Boolean mask per root: the two 'transmitted' modes (reference waves.py:273-289).
+
+    all |Im| > tol : two largest Im;  none: two largest Re;  mixed: forward iff Im > tol or
+    (|Im| <= tol and Re > 0), resolved to exactly two by ranking.
+    """
+    lam = np.stack(roots, axis=-1)
+    im, re = lam.imag, lam.real
+    cplx = np.abs(im) > IM_TOL
+    n_c = cplx.sum(axis=-1, keepdims=True)
+    score = np.where(cplx, np.where(im > 0, 2.0, -2.0), np.where(re > 0, 1.0, -1.0))
+    key1 = np.where(n_c == 4, 0.0, np.where(n_c == 0, 0.0, score))
+    key2 = np.where(n_c == 0, re, im)
+    key3 = re
+    # rank = number of roots strictly "better" (lexicographic, index as final tie-break)
+    rank = np.zeros(lam.shape, dtype=np.int64)
+    for i in range(4):
+        for jx in range(4):
+            if i == jx:
+                continue
+            better = (key1[..., jx] > key1[..., i]) | (
+                (key1[..., jx] == key1[..., i]) & ((key2[..., jx] > key2[..., i]) | (
+                    (key2[..., jx] == key2[..., i]) & ((key3[..., jx] > key3[..., i]) | (
+                        (key3[..., jx] == key3[..., i]) & (jx < i))))))
+            rank[..., i] += better
+    return [rank[..., i] < 2 for i in range(4)], n_c[..., 0]
+
+
+def bairstow(u, v, c3, c2, c1, c0, iters=3):
+    """Newton on (u, v) so that lambda^2 + u lambda + v divides the quartic."""
+    for _ in range(iters):
+        b1 = c3 - u
+        b0 = c2 - u * b1 - v
+        r1 = c1 - u * b0 - v * b1
+        r0 = c0 - v * b0
+        j11 = -b0 - u * (u - b1) + v
+        j12 = u - b1
+        j21 = -v * (u - b1)
+        j22 = v - b0
+        det = j11 * j22 - j12 * j21
+        ok = np.abs(det) > 1e-300
+        idet = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        du = (-r1 * j22 + r0 * j12) * idet
+        dv = (-r0 * j11 + r1 * j21) * idet
+        u, v = u + du, v + dv
+    b1 = c3 - u
+    b0 = c2 - u * b1 - v
+    return u, v, b1, b0
+
+
+def split_spectrum(D, polish=0, bairstow_iters=3):
+    """-> (sf, pf, sb, pb, n_complex): sum/product of forward and backward root pairs."""
+    c3, c2, c1, c0 = charpoly(D)
+    roots = ferrari(c3, c2, c1, c0)
+    if polish:
+        roots = newton_polish(roots, c3, c2, c1, c0, polish)
+    fwd, n_c = classify_forward(roots)
+    sf = sum(np.where(fm, lam, 0.0) for fm, lam in zip(fwd, roots))
+    pf = np.prod([np.where(fm, lam, 1.0) for fm, lam in zip(fwd, roots)], axis=0)
+    u, v, b1, b0 = bairstow(-sf, pf, c3, c2, c1, c0, bairstow_iters)
+    return -u, v, -b1, b0, n_c
+
+
+def projector_coeffs(sf, pf, sb, pb):
+    """h(x) = h0 + h1 x with h q_b = 1 (mod q_f)."""
+    U = sf - sb
+    V = pb - pf
+    R = U * U * pf + U * V * sf + V * V
+    iR = 1.0 / R
+    return (U * sf + V) * iR, -U * iR
+
+
+def apply_q(D, w, s, p):
+    """(D^2 - s D + p I) w, also returns D w."""
+    t1 = matvec(D, w)
+    t2 = matvec(D, t1)
+    return tuple(t2[i] - s * t1[i] + p * w[i] for i in range(4)), t1
+
+
+def project_forward(D, y, sf, pf, sb, pb):
+    """P_f y  (y a 4-tuple), plus D y (reused by callers)."""
+    h0, h1 = projector_coeffs(sf, pf, sb, pb)
+    dy = matvec(D, y)
+    w = tuple(h0 * y[i] + h1 * dy[i] for i in range(4))
+    z, _ = apply_q(D, w, sb, pb)
+    return z, dy
+
+
+def pair_exponential(s, p, cfac):
+    """(A, B) with exp(cfac * K) = A I + B (K - m I), K having root pair (sum s, product p)."""
+    m = 0.5 * s
+    h2 = m * m - p
+    h = np.sqrt(h2)
+    z = cfac * h
+    small = np.abs(z) < 0.25
+    # general branch from the two individual exponentials (no 0*inf hazards)
+    e_p = np.exp(cfac * (m + h))
+    e_m = np.exp(cfac * (m - h))
+    A_g = 0.5 * (e_p + e_m)
+    hs = np.where(small, 1.0, h)
+    B_g = 0.5 * (e_p - e_m) / hs
+    # confluent branch: series in z^2
+    z2 = z * z
+    ch = 1.0 + z2 / 2.0 * (1.0 + z2 / 12.0 * (1.0 + z2 / 30.0 * (1.0 + z2 / 56.0 * (1.0 + z2 / 90.0))))
+    sh = 1.0 + z2 / 6.0 * (1.0 + z2 / 20.0 * (1.0 + z2 / 42.0 * (1.0 + z2 / 72.0 * (1.0 + z2 / 110.0))))
+    em = np.exp(cfac * m)
+    A = np.where(small, em * ch, A_g)
+    B = np.where(small, em * cfac * sh, B_g)
+    return A, B, m
+
+
+def _expm1c(x):
+    """(exp(x) - 1) / x with a series for small |x|."""
+    small = np.abs(x) < 0.5
+    xs = np.where(small, x, 1.0)
+    ser = 1.0 + xs / 2.0 * (1.0 + xs / 3.0 * (1.0 + xs / 4.0 * (1.0 + xs / 5.0 * (1.0 + xs / 6.0 * (
+        1.0 + xs / 7.0 * (1.0 + xs / 8.0 * (1.0 + xs / 9.0 * (1.0 + xs / 10.0 * (1.0 + xs / 11.0 * (
+            1.0 + xs / 12.0 * (1.0 + xs / 13.0 * (1.0 + xs / 14.0))))))))))))
+    xl = np.where(small, 1.0, x)
+    return np.where(small, ser, (np.exp(xl) - 1.0) / xl)
+
+
+def pair_modes(s, p, cfac):
+    """Order the root pair by |exp(cfac*lambda)|: returns (lam_small, phi_small, dd, separated)
+    with exp(cfac K) = phi_small I + dd (K - lam_small I); ``separated`` = the two exponentials
+    differ by more than a factor e."""
+    m = 0.5 * s
+    h = np.sqrt(m * m - p)
+    swap = (cfac * h).real < 0.0
+    h = np.where(swap, -h, h)          # now Re(cfac*h) >= 0: lam_big = m + h
+    lam_s, lam_g = m - h, m + h
+    phi_s, phi_g = np.exp(cfac * lam_s), np.exp(cfac * lam_g)
+    x = 2.0 * cfac * h
+    small = np.abs(x) < 0.5
+    dd_direct = (phi_g - phi_s) / np.where(small, 1.0, lam_g - lam_s)
+    dd = np.where(small, cfac * phi_s * _expm1c(np.where(small, x, 0.0)), dd_direct)
+    return lam_s, phi_s, dd, x.real > 1.0
+
+
+def _rank1_clean(r0, r1):
+    """Project the (theoretically rank-one) 4x2 matrix [r0 r1] onto rank one: keep the
+    larger column as the direction, replace the other by its component along it."""
+    n0 = sum(np.abs(x) ** 2 for x in r0)
+    n1 = sum(np.abs(x) ** 2 for x in r1)
+    first = n0 >= n1
+    v = tuple(np.where(first, a, b) for a, b in zip(r0, r1))
+    w = tuple(np.where(first, b, a) for a, b in zip(r0, r1))
+    nv = np.where(first, n0, n1)
+    dot = sum(np.conj(a) * b for a, b in zip(v, w))
+    beta = np.where(nv > 0, dot / np.where(nv > 0, nv, 1.0), 0.0)
+    wclean = tuple(beta * a for a in v)
+    c0 = tuple(np.where(first, a, b) for a, b in zip(v, wclean))
+    c1 = tuple(np.where(first, b, a) for a, b in zip(v, wclean))
+    return c0, c1
+
+
+def block_exp_apply(D, Z, s, p, cfac, clean=True):
+    """exp(cfac D) applied to the two columns Z (which lie in the invariant subspace whose
+    root pair has sum s / product p):  phi_s Z + dd (D - lam_s) Z, the second term forced
+    to rank one (it is a multiple of the faster-growing eigenvector)."""
+    lam_s, phi_s, dd, separated = pair_modes(s, p, cfac)
+    R = []
+    for z in Z:
+        dz = matvec(D, z)
+        R.append(tuple(dz[i] - lam_s * z[i] for i in range(4)))
+    if clean:
+        # only when the pair's exponentials differ by more than e: then lam_s is a
+        # well-resolved simple root and (D - lam_s) Z is rank one up to rounding
+        C = _rank1_clean(R[0], R[1])
+        R = [tuple(np.where(separated, C[k][i], R[k][i]) for i in range(4)) for k in range(2)]
+    return [tuple(phi_s * Z[k][i] + dd * R[k][i] for i in range(4)) for k in range(2)]
+
+
+def film_transfer(D, Y, spec, cfac, clean=True):
+    """exp(cfac D) applied to both columns of Y (list of two 4-tuples). Unnormalised."""
+    sf, pf, sb, pb = spec
+    zf, zb = [], []
+    for y in Y:
+        z, _ = project_forward(D, y, sf, pf, sb, pb)
+        zf.append(z)
+        zb.append(tuple(y[i] - z[i] for i in range(4)))
+    gf = block_exp_apply(D, zf, sf, pf, cfac, clean)
+    gb = block_exp_apply(D, zb, sb, pb, cfac, clean)
+    return [tuple(gf[k][i] + gb[k][i] for i in range(4)) for k in range(2)]
+
+
+def _inv2(m00, m01, m10, m11):
+    det = m00 * m11 - m01 * m10
+    idet = 1.0 / det
+    return m11 * idet, -m01 * idet, -m10 * idet, m00 * idet
+
+
+def film_stable(D, Y, spec, cfac, rows=(0, 1)):
+    """Stable (scattering-equivalent) propagation of the plane spanned by Y through a film.
+
+    Returns the renormalised plane X_f + G_b Z_b N (L G_f^-1 X_f) using only decaying
+    exponentials, and the 2x2 normalisation C = N g_f^-1 that maps
+    top coordinates to bottom coordinates.
+    """
+    sf, pf, sb, pb = spec
+    Afi, Bfi, mf = pair_exponential(sf, pf, -cfac)  # G_f^{-1} on F : exp(-cfac K_f), decaying
+    Ab, Bb, mb = pair_exponential(sb, pb, cfac)     # G_b on B     : exp(+cfac K_b), decaying
+    zf, zb = [], []
+    for y in Y:
+        z, _ = project_forward(D, y, sf, pf, sb, pb)
+        zf.append(z)
+        zb.append(tuple(y[i] - z[i] for i in range(4)))
+    r0, r1 = rows
+    n00, n01, n10, n11 = _inv2(zf[0][r0], zf[1][r0], zf[0][r1], zf[1][r1])
+    xf = [tuple(zf[0][i] * n00 + zf[1][i] * n10 for i in range(4)),
+          tuple(zf[0][i] * n01 + zf[1][i] * n11 for i in range(4))]
+    xb = [tuple(zb[0][i] * n00 + zb[1][i] * n10 for i in range(4)),
+          tuple(zb[0][i] * n01 + zb[1][i] * n11 for i in range(4))]
+    # g = L G_f^-1 X_f   (2x2)
+    gcols = []
+    for x in xf:
+        dx = matvec(D, x)
+        gx = tuple((Afi - Bfi * mf) * x[i] + Bfi * dx[i] for i in range(4))
+        gcols.append((gx[r0], gx[r1]))
+    # G_b X_b
+    gb = []
+    for x in xb:
+        dx = matvec(D, x)
+        gb.append(tuple((Ab - Bb * mb) * x[i] + Bb * dx[i] for i in range(4)))
+    out = [tuple(xf[cidx][i] + gb[0][i] * gcols[cidx][0] + gb[1][i] * gcols[cidx][1] for i in range(4))
+           for cidx in range(2)]
+    return out
+
+
+def substrate_plane(D, spec):
+    """Basis of the forward invariant subspace: P_f [e0 e1]."""
+    sf, pf, sb, pb = spec
+    one = np.ones_like(sf)
+    zero = np.zeros_like(sf)
+    cols = []
+    for idx in range(2):
+        y = tuple(one if i == idx else zero for i in range(4))
+        z, _ = project_forward(D, y, sf, pf, sb, pb)
+        cols.append(z)
+    return cols
+
+
+# ----------------------------------------------------------------------------- isotropic
+def iso_delta(k, eps, mu):
+    """Isotropic Berreman entries in the 9-parameter form."""
+    z = np.zeros_like(eps + k)
+    k2 = k * k
+    return (z, z, z, mu - k2 / eps, z, -mu + z, z, k2 / mu - eps, eps + z)
+
+
+def iso_film_transfer(k, eps, mu, Y, cfac):
+    """exp(cfac D) Y for an isotropic film: D^2 = kz^2 I  =>  cosh(c kz) I + c sinhc(c kz) D."""
+    D = iso_delta(k, eps, mu)
+    kz2 = eps * mu - k * k
+    A, B, _ = pair_exponential(np.zeros_like(kz2), -kz2, cfac)  # pair (+kz, -kz): s=0, p=-kz^2
+    out = []
+    for y in Y:
+        dy = matvec(D, y)
+        out.append(tuple(A * y[i] + B * dy[i] for i in range(4)))
+    return out
+
+
+def iso_forward_kz(k, eps, mu):
+    kz = np.sqrt(eps * mu - k * k + 0j)
+    fwd = np.where(np.abs(kz.imag) > IM_TOL, kz.imag > 0, kz.real > 0)
+    return np.where(fwd, kz, -kz)
+
+
+def iso_film_stable(k, eps, mu, Y, cfac, rows=(0, 1)):
+    D = iso_delta(k, eps, mu)
+    kz = iso_forward_kz(k, eps, mu)
+    ikz = 1.0 / kz
+    phase2 = np.exp(-2.0 * cfac * kz)  # exp(2 i tau kz), decaying (cfac = -i tau)
+    zf, zb = [], []
+    for y in Y:
+        dy = matvec(D, y)
+        f = tuple(0.5 * (y[i] + dy[i] * ikz) for i in range(4))
+        zf.append(f)
+        zb.append(tuple(y[i] - f[i] for i in range(4)))
+    r0, r1 = rows
+    n00, n01, n10, n11 = _inv2(zf[0][r0], zf[1][r0], zf[0][r1], zf[1][r1])
+    out = []
+    for (ca, cb) in ((n00, n10), (n01, n11)):
+        out.append(tuple(zf[0][i] * ca + zf[1][i] * cb + phase2 * (zb[0][i] * ca + zb[1][i] * cb)
+                         for i in range(4)))
+    return out
+
+
+# ----------------------------------------------------------------------------- ambient + reduction
+def exit_iso_plane(cf, n_exit):
+    """Columns 0 and 2 of the isotropic exit matrix (reference layers.py:190-238)."""
+    z = np.zeros_like(cf)
+    o = np.ones_like(cf)
+    return [(z, o, -n_exit * cf, z), (cf, z, z, n_exit * o)]
+
+
+def reflect_from_plane(Y, inv_c, inv_nc, inv_n):
+    """Prism matrix applied to the plane + 2x2 minors (reference layers.py:109-152,
+    structure.py:285-304).  The common factor 1/2 of the prism matrix cancels."""
+    g = []
+    for y in Y:
+        g.append((y[1] - y[2] * inv_nc, y[1] + y[2] * inv_nc,
+                  y[0] * inv_c + y[3] * inv_n, -y[0] * inv_c + y[3] * inv_n))
+    (g00, g10, g20, g30), (g02, g12, g22, g32) = g
+    bottom = g00 * g22 - g02 * g20
+    ib = 1.0 / bottom
+    r_pp = (g00 * g32 - g30 * g02) * ib
+    r_ps = (g00 * g12 - g10 * g02) * ib
+    r_sp = (g30 * g22 - g32 * g20) * ib
+    r_ss = (g10 * g22 - g12 * g20) * ib
+    return r_pp, r_ps, r_sp, r_ss
+
+
+def mueller(pp, ps, sp, ss):
+    """Real Mueller matrix M = Re(A F A^-1) written out (reference mueller.py:266-307)."""
+    cj = np.conj
+    F = [[pp * cj(pp), pp * cj(ps), ps * cj(pp), ps * cj(ps)],
+         [pp * cj(sp), pp * cj(ss), ps * cj(sp), ps * cj(ss)],
+         [sp * cj(pp), sp * cj(ps), ss * cj(pp), ss * cj(ps)],
+         [sp * cj(sp), sp * cj(ss), ss * cj(sp), ss * cj(ss)]]
+    rows = [[F[0][c] + F[3][c] for c in range(4)], [F[0][c] - F[3][c] for c in range(4)],
+            [F[1][c] + F[2][c] for c in range(4)], [1j * (F[1][c] - F[2][c]) for c in range(4)]]
+    M = np.empty(np.shape(pp) + (4, 4))
+    for r in range(4):
+        c0, c1, c2, c3 = rows[r]
+        M[..., r, 0] = 0.5 * (c0 + c3).real
+        M[..., r, 1] = 0.5 * (c0 - c3).real
+        M[..., r, 2] = 0.5 * (c1 + c2).real
+        M[..., r, 3] = (0.5j * (c2 - c1)).real
+    return M
