@@ -1,0 +1,110 @@
+"""ctypes binding of ``libho_b200.so`` (C ABI declared in ``include/ho_b200.h``).
+
+The library is the product: if it is missing or fails to load, importing this module
+raises -- there is no Python/NumPy fallback for the hot path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+HO_MAX_LAYERS = 24
+HO_ABI_VERSION = 1
+
+HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
+HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
+
+
+class c128(C.Structure):
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_eps", C.c_int32), ("n_mu", C.c_int32), ("mu_scalar", C.c_int32),
+        ("n_beta", C.c_int32), ("n_thickness", C.c_int32),
+        ("eps", C.c_void_p), ("mu", C.c_void_p),
+        ("cos_beta", C.c_void_p), ("sin_beta", C.c_void_p), ("thickness", C.c_void_p),
+        ("iso_eps", c128), ("iso_mu", c128),
+        ("exit_cos", C.c_void_p), ("exit_n", C.c_double),
+    ]
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("A", C.c_int32), ("B", C.c_int32), ("F", C.c_int32), ("T", C.c_int32),
+        ("n_layers", C.c_int32), ("backend", C.c_int32),
+        ("kx", C.c_void_p), ("k0", C.c_void_p),
+        ("prism_inv_cos", C.c_void_p), ("prism_inv_ncos", C.c_void_p),
+        ("prism_inv_n", C.c_double),
+        ("layers", LayerDesc * HO_MAX_LAYERS),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [
+        ("r_pp", C.c_void_p), ("r_ps", C.c_void_p), ("r_sp", C.c_void_p), ("r_ss", C.c_void_p),
+        ("mueller", C.c_void_p), ("stokes", C.c_void_p),
+        ("incident_stokes", C.c_double * 4),
+    ]
+
+
+class OutputsF32(C.Structure):
+    _fields_ = [
+        ("r_pp", C.c_void_p), ("r_ps", C.c_void_p), ("r_sp", C.c_void_p), ("r_ss", C.c_void_p),
+        ("mueller", C.c_void_p),
+    ]
+
+
+EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_measure_fp64_peak", "ho_launch_count",
+           "ho_abi_version", "ho_last_error")
+
+
+def library_path() -> Path:
+    override = os.environ.get("HO_B200_LIB")
+    return Path(override) if override else Path(__file__).resolve().parent / "libho_b200.so"
+
+
+def load():
+    path = library_path()
+    if not path.exists():
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the reflection engine.")
+    lib = C.CDLL(str(path))
+    lib.ho_reflect.argtypes = [C.POINTER(Problem), C.POINTER(Outputs), C.c_int64, C.c_int64, C.c_void_p]
+    lib.ho_reflect.restype = C.c_int
+    lib.ho_reflect_f32.argtypes = [C.POINTER(Problem), C.POINTER(OutputsF32), C.c_int64, C.c_int64, C.c_void_p]
+    lib.ho_reflect_f32.restype = C.c_int
+    lib.ho_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    lib.ho_measure_fp64_peak.restype = C.c_int
+    lib.ho_launch_count.argtypes = []
+    lib.ho_launch_count.restype = C.c_int64
+    lib.ho_abi_version.argtypes = []
+    lib.ho_abi_version.restype = C.c_int
+    lib.ho_last_error.argtypes = []
+    lib.ho_last_error.restype = C.c_char_p
+    if lib.ho_abi_version() != HO_ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {lib.ho_abi_version()} != expected {HO_ABI_VERSION}")
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(f"libho_b200 error {rc}: {lib().ho_last_error().decode()}")

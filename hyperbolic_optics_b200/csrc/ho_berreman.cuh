@@ -1,0 +1,420 @@
+// ho_berreman.cuh -- per-point physics of the fused reflection kernel.
+//
+// One thread owns one batch point and keeps everything in registers:
+//   rotate eps/mu about z  ->  structured Berreman matrix  ->  characteristic quartic
+//   ->  forward/backward spectral split  ->  spectral projector  ->  running 4x2 "plane"
+// swept right-to-left (exit -> prism), then the 2x2 reflection block and the Mueller matrix.
+// The algorithm never forms eigenvectors; see DESIGN.md section 4 and tools/algo_model.py
+// (the NumPy statement-for-statement model this file was written against).
+#pragma once
+#include "ho_math.cuh"
+
+namespace ho {
+
+// Berreman matrix for symmetric eps, mu (reference waves.py:221-245):
+//   [[a, b, c, d], [0, e, f, -c], [g, h, e, -b], [j, -g, 0, a]]
+template <typename T> struct Delta { cx<T> a, b, c, d, e, f, g, h, j; };
+template <typename T> struct Vec4 { cx<T> v0, v1, v2, v3; };
+template <typename T> struct Sym6 { cx<T> xx, xy, xz, yy, yz, zz; };
+// sums / products of the forward and backward root pairs
+template <typename T> struct Spectrum { cx<T> sf, pf, sb, pb; };
+
+template <typename T> __device__ __forceinline__ Vec4<T> axpy(cx<T> s, const Vec4<T>& x, const Vec4<T>& y) {
+  Vec4<T> r; r.v0 = fma(s, x.v0, y.v0); r.v1 = fma(s, x.v1, y.v1); r.v2 = fma(s, x.v2, y.v2); r.v3 = fma(s, x.v3, y.v3); return r;
+}
+template <typename T> __device__ __forceinline__ Vec4<T> scale(cx<T> s, const Vec4<T>& x) {
+  Vec4<T> r; r.v0 = s * x.v0; r.v1 = s * x.v1; r.v2 = s * x.v2; r.v3 = s * x.v3; return r;
+}
+template <typename T> __device__ __forceinline__ Vec4<T> sub(const Vec4<T>& x, const Vec4<T>& y) {
+  Vec4<T> r; r.v0 = x.v0 - y.v0; r.v1 = x.v1 - y.v1; r.v2 = x.v2 - y.v2; r.v3 = x.v3 - y.v3; return r;
+}
+template <typename T> __device__ __forceinline__ Vec4<T> add(const Vec4<T>& x, const Vec4<T>& y) {
+  Vec4<T> r; r.v0 = x.v0 + y.v0; r.v1 = x.v1 + y.v1; r.v2 = x.v2 + y.v2; r.v3 = x.v3 + y.v3; return r;
+}
+template <typename T> __device__ __forceinline__ T norm2(const Vec4<T>& x) {
+  return norm2(x.v0) + norm2(x.v1) + norm2(x.v2) + norm2(x.v3);
+}
+template <typename T> __device__ __forceinline__ cx<T> dotc(const Vec4<T>& x, const Vec4<T>& y) {  // x^H y
+  return cmulc(x.v0, y.v0) + cmulc(x.v1, y.v1) + cmulc(x.v2, y.v2) + cmulc(x.v3, y.v3);
+}
+template <typename T> __device__ __forceinline__ Vec4<T> sel(bool c, const Vec4<T>& a, const Vec4<T>& b) {
+  Vec4<T> r; r.v0 = sel(c, a.v0, b.v0); r.v1 = sel(c, a.v1, b.v1); r.v2 = sel(c, a.v2, b.v2); r.v3 = sel(c, a.v3, b.v3); return r;
+}
+
+// Rz(beta) S Rz(beta)^T for a packed symmetric tensor (reference layers.py:55-66, 411-417)
+template <typename T> __device__ __forceinline__ Sym6<T> rotate_z(const Sym6<T>& s, T cb, T sb) {
+  T c2 = cb * cb, s2 = sb * sb, cs = cb * sb;
+  Sym6<T> r;
+  r.xx = c2 * s.xx - (T(2) * cs) * s.xy + s2 * s.yy;
+  r.xy = cs * (s.xx - s.yy) + (c2 - s2) * s.xy;
+  r.xz = cb * s.xz - sb * s.yz;
+  r.yy = s2 * s.xx + (T(2) * cs) * s.xy + c2 * s.yy;
+  r.yz = sb * s.xz + cb * s.yz;
+  r.zz = s.zz;
+  return r;
+}
+
+template <typename T> __device__ __forceinline__ Delta<T> berreman(T k, const Sym6<T>& e, const Sym6<T>& m) {
+  cx<T> ie = recip(e.zz), im = recip(m.zz);
+  T k2 = k * k;
+  Delta<T> D;
+  D.a = -(k * (e.xz * ie));
+  D.b = k * (m.yz * im - e.yz * ie);
+  D.c = m.xy - m.yz * m.xz * im;
+  D.d = m.yy - m.yz * m.yz * im - k2 * ie;
+  D.e = -(k * (m.xz * im));
+  D.f = m.xz * m.xz * im - m.xx;
+  D.g = e.yz * e.xz * ie - e.xy;
+  D.h = k2 * im - e.yy + e.yz * e.yz * ie;
+  D.j = e.xx - e.xz * e.xz * ie;
+  return D;
+}
+
+template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T>& D, const Vec4<T>& v) {
+  Vec4<T> r;
+  r.v0 = fma(D.d, v.v3, fma(D.c, v.v2, fma(D.b, v.v1, D.a * v.v0)));
+  r.v1 = fma(D.f, v.v2, D.e * v.v1) - D.c * v.v3;
+  r.v2 = fma(D.e, v.v2, fma(D.h, v.v1, D.g * v.v0)) - D.b * v.v3;
+  r.v3 = fma(D.a, v.v3, D.j * v.v0) - D.g * v.v1;
+  return r;
+}
+
+// det(lambda I - D) = lambda^4 + c3 lambda^3 + c2 lambda^2 + c1 lambda + c0
+template <typename T> __device__ __forceinline__ void charpoly(const Delta<T>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
+  cx<T> a2 = D.a * D.a, e2 = D.e * D.e, cg = D.c * D.g, dj = D.d * D.j, fh = D.f * D.h;
+  cx<T> bcj = D.b * D.c * D.j, bf = D.b * D.f, ae = D.a * D.e;
+  c3 = T(-2) * (D.a + D.e);
+  c2 = a2 + T(4) * ae - T(2) * cg - dj + e2 - fh;
+  c1 = T(-2) * (a2 * D.e - D.a * cg + D.a * e2 - D.a * fh - bcj + bf * D.g - D.e * cg - D.e * dj);
+  c0 = a2 * e2 - a2 * fh + T(2) * (D.a * bf * D.g) - T(2) * (ae * cg) + D.b * bf * D.j - T(2) * (D.e * bcj)
+       + cg * cg + D.c * D.c * D.h * D.j - e2 * dj + D.d * D.f * D.g * D.g + dj * fh;
+}
+
+// roots of y^2 + bq y + cq without cancellation
+template <typename T> __device__ __forceinline__ void quad_roots(cx<T> bq, cx<T> cq, cx<T>& y0, cx<T>& y1) {
+  cx<T> sq = csqrt(bq * bq - T(4) * cq);
+  bool plus = cmulc(bq, sq).re >= T(0);
+  cx<T> t = T(-0.5) * (plus ? bq + sq : bq - sq);
+  y0 = t;
+  y1 = (norm2(t) > T(0)) ? cq / t : mk<T>(T(0), T(0));
+}
+
+// Ferrari / Cardano closed form: start values for the spectral split
+template <typename T> __device__ __forceinline__ void ferrari(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> lam[4]) {
+  cx<T> q3 = T(0.25) * c3;
+  cx<T> q32 = q3 * q3;
+  cx<T> p = c2 - T(6) * q32;
+  cx<T> q = c1 - T(2) * (q3 * c2) + T(8) * (q32 * q3);
+  cx<T> r = c0 - q3 * c1 + q32 * c2 - T(3) * (q32 * q32);
+  cx<T> p2 = p * p;
+  cx<T> P = T(-1.0 / 12.0) * p2 - r;
+  cx<T> Q = T(-1.0 / 108.0) * (p2 * p) + T(1.0 / 3.0) * (p * r) - T(0.125) * (q * q);
+  cx<T> sq = csqrt(T(0.25) * (Q * Q) + T(1.0 / 27.0) * (P * P * P));
+  cx<T> ua = T(-0.5) * Q + sq, ub = T(-0.5) * Q - sq;
+  cx<T> u = ccbrt(norm2(ua) >= norm2(ub) ? ua : ub);
+  const cx<T> w1 = mk<T>(T(-0.5), T(0.86602540378443864676));
+  const cx<T> w2 = mk<T>(T(-0.5), T(-0.86602540378443864676));
+  cx<T> third_p = T(1.0 / 3.0) * p;
+  cx<T> m = mk<T>(T(0), T(0));
+  T best = T(-1);
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    cx<T> uk = (kk == 0) ? u : (kk == 1 ? u * w1 : u * w2);
+    cx<T> tk = uk;
+    if (norm2(uk) > T(0)) tk = uk - T(1.0 / 3.0) * (P / uk);
+    cx<T> mk_ = tk - third_p;
+    T ak = norm2(mk_);
+    if (ak > best) { best = ak; m = mk_; }
+  }
+  cx<T> alpha = csqrt(T(2) * m);
+  cx<T> qa = (norm2(alpha) > T(0)) ? T(0.5) * (q / alpha) : mk<T>(T(0), T(0));
+  cx<T> base = T(0.5) * p + m;
+  cx<T> y0, y1, y2, y3;
+  quad_roots(alpha, base - qa, y0, y1);
+  quad_roots(-alpha, base + qa, y2, y3);
+  lam[0] = y0 - q3; lam[1] = y1 - q3; lam[2] = y2 - q3; lam[3] = y3 - q3;
+}
+
+// Forward ("transmitted") pair selection, reference waves.py:273-289: all |Im| > 1e-9 -> two
+// largest Im; none -> two largest Re; mixed -> Im > tol, or |Im| <= tol and Re > 0 (ranked).
+template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4], bool fwd[4]) {
+  const T tol = T(1e-9);
+  int n_c = 0;
+  bool cplx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { cplx[i] = ho_abs(lam[i].im) > tol; n_c += cplx[i] ? 1 : 0; }
+  T k1[4], k2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    T score = cplx[i] ? (lam[i].im > T(0) ? T(2) : T(-2)) : (lam[i].re > T(0) ? T(1) : T(-1));
+    k1[i] = (n_c == 4 || n_c == 0) ? T(0) : score;
+    k2[i] = (n_c == 0) ? lam[i].re : lam[i].im;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int rank = 0;
+#pragma unroll
+    for (int jx = 0; jx < 4; ++jx) {
+      if (jx == i) continue;
+      bool better = (k1[jx] > k1[i]) ||
+                    (k1[jx] == k1[i] && ((k2[jx] > k2[i]) ||
+                                         (k2[jx] == k2[i] && ((lam[jx].re > lam[i].re) ||
+                                                              (lam[jx].re == lam[i].re && jx < i)))));
+      rank += better ? 1 : 0;
+    }
+    fwd[i] = rank < 2;
+  }
+}
+
+// Newton (Bairstow) on the quadratic factor lambda^2 + u lambda + v of the quartic; the
+// complementary factor lambda^2 + b1 lambda + b0 follows by deflation.
+template <typename T> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T>& D) {
+  cx<T> c3, c2, c1, c0;
+  charpoly(D, c3, c2, c1, c0);
+  cx<T> lam[4];
+  ferrari(c3, c2, c1, c0, lam);
+  bool fwd[4];
+  classify(lam, fwd);
+  cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
+  }
+  cx<T> u = -sf, v = pf, b1, b0;
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    b1 = c3 - u;
+    b0 = c2 - u * b1 - v;
+    cx<T> r1 = c1 - u * b0 - v * b1;
+    cx<T> r0 = c0 - v * b0;
+    cx<T> umb = u - b1;
+    cx<T> j11 = v - b0 - u * umb;
+    cx<T> j12 = umb;
+    cx<T> j21 = -(v * umb);
+    cx<T> j22 = v - b0;
+    cx<T> det = j11 * j22 - j12 * j21;
+    if (norm2(det) > T(0)) {
+      cx<T> idet = recip(det);
+      u = u + (r0 * j12 - r1 * j22) * idet;
+      v = v + (r1 * j21 - r0 * j11) * idet;
+    }
+  }
+  b1 = c3 - u;
+  b0 = c2 - u * b1 - v;
+  Spectrum<T> s;
+  s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
+  return s;
+}
+
+// h(x) = h0 + h1 x with h q_b = 1 (mod q_f): the forward spectral projector is q_b(D) h(D)
+template <typename T> __device__ __forceinline__ void projector_coeffs(const Spectrum<T>& s, cx<T>& h0, cx<T>& h1) {
+  cx<T> U = s.sf - s.sb, V = s.pb - s.pf;
+  cx<T> R = U * U * s.pf + U * V * s.sf + V * V;
+  cx<T> iR = recip(R);
+  h0 = (U * s.sf + V) * iR;
+  h1 = -(U * iR);
+}
+
+// z = P_f y, also returns dy = D y
+template <typename T> __device__ __forceinline__ Vec4<T> project_forward(const Delta<T>& D, const Spectrum<T>& s, cx<T> h0, cx<T> h1,
+                                                                        const Vec4<T>& y, Vec4<T>& dy) {
+  dy = matvec(D, y);
+  Vec4<T> w = axpy(h1, dy, scale(h0, y));
+  Vec4<T> t1 = matvec(D, w);
+  Vec4<T> t2 = matvec(D, t1);
+  return axpy(s.pb, w, axpy(-s.sb, t1, t2));
+}
+
+// Root pair (sum s, product p) ordered by |exp(c lambda)|: exp(c K) = phi_s I + dd (K - lam_s I)
+template <typename T> __device__ __forceinline__ void pair_modes(cx<T> s, cx<T> p, cx<T> c, cx<T>& lam_s, cx<T>& phi_s, cx<T>& dd, bool& separated) {
+  cx<T> m = T(0.5) * s;
+  cx<T> h = csqrt(m * m - p);
+  if ((c * h).re < T(0)) h = -h;
+  lam_s = m - h;
+  cx<T> lam_g = m + h;
+  phi_s = cexp(c * lam_s);
+  cx<T> x = T(2) * (c * h);
+  separated = x.re > T(1);
+  if (norm2(x) < T(0.25)) {
+    dd = c * phi_s * expm1c(x);
+  } else {
+    dd = (cexp(c * lam_g) - phi_s) / (lam_g - lam_s);
+  }
+}
+
+// Project the (theoretically rank-one) 4x2 matrix [r0 r1] onto rank one.
+template <typename T> __device__ __forceinline__ void rank1_clean(Vec4<T>& r0, Vec4<T>& r1) {
+  T n0 = norm2(r0), n1 = norm2(r1);
+  bool first = n0 >= n1;
+  Vec4<T> v = sel(first, r0, r1), w = sel(first, r1, r0);
+  T nv = first ? n0 : n1;
+  cx<T> beta = mk<T>(T(0), T(0));
+  if (nv > T(0)) beta = (T(1) / nv) * dotc(v, w);
+  Vec4<T> wc = scale(beta, v);
+  r0 = sel(first, v, wc);
+  r1 = sel(first, wc, v);
+}
+
+// exp(c D) applied to two columns lying in one invariant subspace (root pair s, p)
+template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> s, cx<T> p, cx<T> c, const Vec4<T>& z0, const Vec4<T>& z1,
+                                                                     const Vec4<T>& dz0, const Vec4<T>& dz1, Vec4<T>& o0, Vec4<T>& o1) {
+  cx<T> lam_s, phi_s, dd;
+  bool separated;
+  pair_modes(s, p, c, lam_s, phi_s, dd, separated);
+  Vec4<T> r0 = axpy(-lam_s, z0, dz0), r1 = axpy(-lam_s, z1, dz1);
+  if (separated) rank1_clean(r0, r1);
+  o0 = axpy(dd, r0, scale(phi_s, z0));
+  o1 = axpy(dd, r1, scale(phi_s, z1));
+}
+
+// exp(c D) Y, unnormalised (transfer-matrix semantics: overflows for thick evanescent layers)
+template <typename T> __device__ __forceinline__ void film_transfer(const Delta<T>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
+  cx<T> h0, h1;
+  projector_coeffs(s, h0, h1);
+  Vec4<T> dy0, dy1;
+  Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy0);
+  Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy1);
+  Vec4<T> dzf0 = matvec(D, zf0), dzf1 = matvec(D, zf1);
+  Vec4<T> f0, f1, b0, b1;
+  block_exp_apply(s.sf, s.pf, c, zf0, zf1, dzf0, dzf1, f0, f1);
+  block_exp_apply(s.sb, s.pb, c, sub(y0, zf0), sub(y1, zf1), sub(dy0, dzf0), sub(dy1, dzf1), b0, b1);
+  y0 = add(f0, b0);
+  y1 = add(f1, b1);
+}
+
+// 2x2 inverse of [[m00, m01], [m10, m11]]
+template <typename T> __device__ __forceinline__ void inv2(cx<T> m00, cx<T> m01, cx<T> m10, cx<T> m11, cx<T>& n00, cx<T>& n01, cx<T>& n10, cx<T>& n11) {
+  cx<T> idet = recip(m00 * m11 - m01 * m10);
+  n00 = m11 * idet; n01 = -(m01 * idet); n10 = -(m10 * idet); n11 = m00 * idet;
+}
+
+// A I + B (D - lam I) applied to x, given dx = D x
+template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx<T> dd, cx<T> lam, const Vec4<T>& x, const Vec4<T>& dx) {
+  return axpy(dd, axpy(-lam, x, dx), scale(phi, x));
+}
+
+// Stable propagation of the plane span(Y) through a film: only decaying exponentials.
+// Renormalises so that rows (Ex, Ey) of the forward part are the identity.
+template <typename T> __device__ __forceinline__ void film_stable(const Delta<T>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
+  cx<T> h0, h1;
+  projector_coeffs(s, h0, h1);
+  Vec4<T> dy;
+  Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy);
+  Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy);
+  Vec4<T> zb0 = sub(y0, zf0), zb1 = sub(y1, zf1);
+  cx<T> n00, n01, n10, n11;
+  inv2(zf0.v0, zf1.v0, zf0.v1, zf1.v1, n00, n01, n10, n11);
+  Vec4<T> xf0 = axpy(n10, zf1, scale(n00, zf0)), xf1 = axpy(n11, zf1, scale(n01, zf0));
+  Vec4<T> xb0 = axpy(n10, zb1, scale(n00, zb0)), xb1 = axpy(n11, zb1, scale(n01, zb0));
+  cx<T> lam, phi, dd;
+  bool sep;
+  // g = L exp(-c K_f) X_f  (2x2): forward modes run back down the film, decaying
+  pair_modes(s.sf, s.pf, -c, lam, phi, dd, sep);
+  Vec4<T> g0 = lin_apply(phi, dd, lam, xf0, matvec(D, xf0));
+  Vec4<T> g1 = lin_apply(phi, dd, lam, xf1, matvec(D, xf1));
+  // exp(+c K_b) X_b: backward modes up the film, decaying
+  pair_modes(s.sb, s.pb, c, lam, phi, dd, sep);
+  Vec4<T> e0 = lin_apply(phi, dd, lam, xb0, matvec(D, xb0));
+  Vec4<T> e1 = lin_apply(phi, dd, lam, xb1, matvec(D, xb1));
+  y0 = axpy(g0.v1, e1, axpy(g0.v0, e0, xf0));
+  y1 = axpy(g1.v1, e1, axpy(g1.v0, e0, xf1));
+}
+
+// Forward invariant subspace of a semi-infinite crystal: P_f [e0 e1]
+template <typename T> __device__ __forceinline__ void substrate_plane(const Delta<T>& D, const Spectrum<T>& s, Vec4<T>& y0, Vec4<T>& y1) {
+  cx<T> h0, h1;
+  projector_coeffs(s, h0, h1);
+  const cx<T> one = mk<T>(T(1), T(0)), zero = mk<T>(T(0), T(0));
+  Vec4<T> e0, e1, dy;
+  e0.v0 = one; e0.v1 = zero; e0.v2 = zero; e0.v3 = zero;
+  e1.v0 = zero; e1.v1 = one; e1.v2 = zero; e1.v3 = zero;
+  y0 = project_forward(D, s, h0, h1, e0, dy);
+  y1 = project_forward(D, s, h0, h1, e1, dy);
+}
+
+// ---- isotropic layers: D^2 = kz^2 I, closed forms (reference-equivalent) ----
+template <typename T> __device__ __forceinline__ Vec4<T> iso_matvec(cx<T> d, cx<T> f, cx<T> h, cx<T> j, const Vec4<T>& v) {
+  Vec4<T> r; r.v0 = d * v.v3; r.v1 = f * v.v2; r.v2 = h * v.v1; r.v3 = j * v.v0; return r;
+}
+
+template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, cx<T> mu, cx<T> c, bool stable, Vec4<T>& y0, Vec4<T>& y1) {
+  T k2 = k * k;
+  cx<T> d = mu - k2 * recip(eps), f = -mu, h = k2 * recip(mu) - eps, j = eps;
+  cx<T> kz2 = eps * mu - k2;
+  Vec4<T> dy0 = iso_matvec(d, f, h, j, y0), dy1 = iso_matvec(d, f, h, j, y1);
+  if (!stable) {
+    // exp(c D) = cosh(c kz) I + c sinhc(c kz) D  (even in kz: no branch choice needed)
+    cx<T> kz = csqrt(kz2);
+    cx<T> z = c * kz, A, B;
+    if (norm2(z) < T(0.0625)) {
+      cx<T> z2 = z * z;
+      const cx<T> one = mk<T>(T(1), T(0));
+      cx<T> ch = fma(T(0.5) * z2, fma(T(1.0 / 12.0) * z2, fma(T(1.0 / 30.0) * z2, fma(T(1.0 / 56.0) * z2, fma(T(1.0 / 90.0) * z2, one, one), one), one), one), one);
+      cx<T> sh = fma(T(1.0 / 6.0) * z2, fma(T(1.0 / 20.0) * z2, fma(T(1.0 / 42.0) * z2, fma(T(1.0 / 72.0) * z2, fma(T(1.0 / 110.0) * z2, one, one), one), one), one), one);
+      A = ch; B = c * sh;
+    } else {
+      cx<T> ep = cexp(z), em = cexp(-z);
+      A = T(0.5) * (ep + em);
+      B = T(0.5) * ((ep - em) / kz);
+    }
+    y0 = axpy(B, dy0, scale(A, y0));
+    y1 = axpy(B, dy1, scale(A, y1));
+    return;
+  }
+  // stable: forward branch of kz by the reference's mode rule (waves.py:273-289)
+  cx<T> kz = csqrt(kz2);
+  bool fwd = (ho_abs(kz.im) > T(1e-9)) ? (kz.im > T(0)) : (kz.re > T(0));
+  if (!fwd) kz = -kz;
+  cx<T> ikz = recip(kz);
+  cx<T> ph2 = cexp(T(-2) * (c * kz));  // exp(2 i tau kz): |.| <= 1
+  Vec4<T> zf0 = scale(mk<T>(T(0.5), T(0)), axpy(ikz, dy0, y0)), zf1 = scale(mk<T>(T(0.5), T(0)), axpy(ikz, dy1, y1));
+  Vec4<T> zb0 = sub(y0, zf0), zb1 = sub(y1, zf1);
+  cx<T> n00, n01, n10, n11;
+  inv2(zf0.v0, zf1.v0, zf0.v1, zf1.v1, n00, n01, n10, n11);
+  y0 = axpy(ph2, axpy(n10, zb1, scale(n00, zb0)), axpy(n10, zf1, scale(n00, zf0)));
+  y1 = axpy(ph2, axpy(n11, zb1, scale(n01, zb0)), axpy(n11, zf1, scale(n01, zf0)));
+}
+
+// columns 0 and 2 of the isotropic exit matrix (reference layers.py:190-238)
+template <typename T> __device__ __forceinline__ void exit_iso_plane(cx<T> cf, T n_exit, Vec4<T>& y0, Vec4<T>& y1) {
+  const cx<T> one = mk<T>(T(1), T(0)), zero = mk<T>(T(0), T(0));
+  y0.v0 = zero; y0.v1 = one; y0.v2 = -(n_exit * cf); y0.v3 = zero;
+  y1.v0 = cf; y1.v1 = zero; y1.v2 = zero; y1.v3 = mk<T>(n_exit, T(0));
+}
+
+// prism rows + 2x2 minors (reference layers.py:109-152, structure.py:285-304); the common 1/2 cancels
+template <typename T> __device__ __forceinline__ void reflect_from_plane(const Vec4<T>& y0, const Vec4<T>& y1, T inv_c, T inv_nc, T inv_n,
+                                                                        cx<T>& r_pp, cx<T>& r_ps, cx<T>& r_sp, cx<T>& r_ss) {
+  cx<T> g00 = y0.v1 - inv_nc * y0.v2, g10 = y0.v1 + inv_nc * y0.v2;
+  cx<T> g20 = inv_c * y0.v0 + inv_n * y0.v3, g30 = inv_n * y0.v3 - inv_c * y0.v0;
+  cx<T> g02 = y1.v1 - inv_nc * y1.v2, g12 = y1.v1 + inv_nc * y1.v2;
+  cx<T> g22 = inv_c * y1.v0 + inv_n * y1.v3, g32 = inv_n * y1.v3 - inv_c * y1.v0;
+  cx<T> ib = recip(g00 * g22 - g02 * g20);
+  r_pp = (g00 * g32 - g30 * g02) * ib;
+  r_ps = (g00 * g12 - g10 * g02) * ib;
+  r_sp = (g30 * g22 - g32 * g20) * ib;
+  r_ss = (g10 * g22 - g12 * g20) * ib;
+}
+
+// Mueller matrix M = Re(A F A^-1), F = J (x) J* in the reference's layout (mueller.py:266-307)
+template <typename T> __device__ __forceinline__ void mueller_from_jones(cx<T> pp, cx<T> ps, cx<T> sp, cx<T> ss, T M[16]) {
+  cx<T> F[4][4];
+  F[0][0] = pp * conj(pp); F[0][1] = pp * conj(ps); F[0][2] = ps * conj(pp); F[0][3] = ps * conj(ps);
+  F[1][0] = pp * conj(sp); F[1][1] = pp * conj(ss); F[1][2] = ps * conj(sp); F[1][3] = ps * conj(ss);
+  F[2][0] = sp * conj(pp); F[2][1] = sp * conj(ps); F[2][2] = ss * conj(pp); F[2][3] = ss * conj(ps);
+  F[3][0] = sp * conj(sp); F[3][1] = sp * conj(ss); F[3][2] = ss * conj(sp); F[3][3] = ss * conj(ss);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    cx<T> c0, c1, c2, c3;
+    if (r == 0) { c0 = F[0][0] + F[3][0]; c1 = F[0][1] + F[3][1]; c2 = F[0][2] + F[3][2]; c3 = F[0][3] + F[3][3]; }
+    else if (r == 1) { c0 = F[0][0] - F[3][0]; c1 = F[0][1] - F[3][1]; c2 = F[0][2] - F[3][2]; c3 = F[0][3] - F[3][3]; }
+    else if (r == 2) { c0 = F[1][0] + F[2][0]; c1 = F[1][1] + F[2][1]; c2 = F[1][2] + F[2][2]; c3 = F[1][3] + F[2][3]; }
+    else { c0 = mul_i(F[1][0] - F[2][0]); c1 = mul_i(F[1][1] - F[2][1]); c2 = mul_i(F[1][2] - F[2][2]); c3 = mul_i(F[1][3] - F[2][3]); }
+    M[4 * r + 0] = T(0.5) * (c0.re + c3.re);
+    M[4 * r + 1] = T(0.5) * (c0.re - c3.re);
+    M[4 * r + 2] = T(0.5) * (c1.re + c2.re);
+    M[4 * r + 3] = T(0.5) * (c1.im - c2.im);  // Re(0.5 i (c2 - c1))
+  }
+}
+
+}  // namespace ho

@@ -1,0 +1,96 @@
+// ho_math.cuh -- register-resident complex arithmetic for the Berreman kernels (sm_100a).
+//
+// Everything here is per-thread scalar code on the FP64 (or FP32) pipe: a batch of tiny
+// independent 4x4 complex problems has no GEMM shape, so no tensor cores / TMEM.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace ho {
+
+template <typename T> struct cx { T re, im; };
+
+template <typename T> __device__ __forceinline__ cx<T> mk(T re, T im) { cx<T> z; z.re = re; z.im = im; return z; }
+template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.re + b.re, a.im + b.im); }
+template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.re - b.re, a.im - b.im); }
+template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a) { return mk<T>(-a.re, -a.im); }
+template <typename T> __device__ __forceinline__ cx<T> operator*(cx<T> a, cx<T> b) {
+  return mk<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+template <typename T> __device__ __forceinline__ cx<T> operator*(T s, cx<T> a) { return mk<T>(s * a.re, s * a.im); }
+template <typename T> __device__ __forceinline__ cx<T> operator*(cx<T> a, T s) { return mk<T>(s * a.re, s * a.im); }
+template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, T s) { return mk<T>(a.re + s, a.im); }
+template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, T s) { return mk<T>(a.re - s, a.im); }
+template <typename T> __device__ __forceinline__ cx<T> conj(cx<T> a) { return mk<T>(a.re, -a.im); }
+template <typename T> __device__ __forceinline__ T norm2(cx<T> a) { return a.re * a.re + a.im * a.im; }
+// a + b*c
+template <typename T> __device__ __forceinline__ cx<T> fma(cx<T> b, cx<T> c, cx<T> a) {
+  return mk<T>(a.re + b.re * c.re - b.im * c.im, a.im + b.re * c.im + b.im * c.re);
+}
+// conj(a)*b
+template <typename T> __device__ __forceinline__ cx<T> cmulc(cx<T> a, cx<T> b) {
+  return mk<T>(a.re * b.re + a.im * b.im, a.re * b.im - a.im * b.re);
+}
+template <typename T> __device__ __forceinline__ cx<T> mul_i(cx<T> a) { return mk<T>(-a.im, a.re); }  // i*a
+template <typename T> __device__ __forceinline__ cx<T> recip(cx<T> a) {
+  T inv = T(1) / norm2(a);
+  return mk<T>(a.re * inv, -a.im * inv);
+}
+template <typename T> __device__ __forceinline__ cx<T> operator/(cx<T> a, cx<T> b) { return a * recip(b); }
+template <typename T> __device__ __forceinline__ cx<T> sel(bool c, cx<T> a, cx<T> b) { return c ? a : b; }
+
+__device__ __forceinline__ double ho_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float ho_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double ho_cbrt(double x) { return cbrt(x); }
+__device__ __forceinline__ float ho_cbrt(float x) { return cbrtf(x); }
+__device__ __forceinline__ double ho_atan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float ho_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double ho_exp(double x) { return exp(x); }
+__device__ __forceinline__ float ho_exp(float x) { return expf(x); }
+__device__ __forceinline__ void ho_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ void ho_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ double ho_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float ho_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double ho_copysign(double x, double y) { return copysign(x, y); }
+__device__ __forceinline__ float ho_copysign(float x, float y) { return copysignf(x, y); }
+
+template <typename T> __device__ __forceinline__ T cabs(cx<T> a) { return ho_sqrt(norm2(a)); }
+
+// principal square root
+template <typename T> __device__ __forceinline__ cx<T> csqrt(cx<T> z) {
+  T r = cabs(z);
+  if (r == T(0)) return mk<T>(T(0), T(0));
+  T t = ho_sqrt(T(0.5) * (r + ho_abs(z.re)));
+  T u = T(0.5) * z.im / t;
+  return (z.re >= T(0)) ? mk<T>(t, u) : mk<T>(ho_abs(u), ho_copysign(t, z.im));
+}
+
+// principal cube root
+template <typename T> __device__ __forceinline__ cx<T> ccbrt(cx<T> z) {
+  T r = cabs(z);
+  T th = ho_atan2(z.im, z.re) * T(1.0 / 3.0);
+  T s, c;
+  ho_sincos(th, &s, &c);
+  T cr = ho_cbrt(r);
+  return mk<T>(cr * c, cr * s);
+}
+
+template <typename T> __device__ __forceinline__ cx<T> cexp(cx<T> z) {
+  T e = ho_exp(z.re);
+  T s, c;
+  ho_sincos(z.im, &s, &c);
+  return mk<T>(e * c, e * s);
+}
+
+// (exp(x) - 1) / x, series below |x| = 0.5
+template <typename T> __device__ __forceinline__ cx<T> expm1c(cx<T> x) {
+  if (norm2(x) < T(0.25)) {
+    cx<T> acc = mk<T>(T(1), T(0));
+#pragma unroll
+    for (int n = 14; n >= 2; --n) acc = fma(x * (T(1) / T(n)), acc, mk<T>(T(1), T(0)));
+    return acc;
+  }
+  return (cexp(x) - T(1)) / x;
+}
+
+}  // namespace ho

@@ -1,0 +1,151 @@
+"""Device side of the planner: upload tables, fill the C descriptor, launch the kernel.
+
+PyTorch is used for exactly three things here: device allocations (``torch.empty`` /
+``tensor.to(device)``), the current CUDA stream handle, and pinned host buffers.  All
+arithmetic happens in ``libho_b200.so``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import plan as P
+
+BACKENDS = {"transfer": nat.HO_BACKEND_TRANSFER, "scattering": nat.HO_BACKEND_SCATTERING}
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("hyperbolic_optics_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback for the reflection engine.")
+    return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+
+class DeviceProblem:
+    """A ``StackPlan`` resident on one GPU plus the filled ``ho_problem_t`` descriptor."""
+
+    def __init__(self, plan: P.StackPlan, backend="transfer", device=None):
+        if backend not in BACKENDS:
+            raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
+        if len(plan.layers) > nat.HO_MAX_LAYERS:
+            raise ValueError(f"at most {nat.HO_MAX_LAYERS} layers below the prism are supported")
+        self.plan = plan
+        self.device = _require_cuda(device)
+        self._keep = []
+        # one packed arena per dtype keeps the upload to two H2D copies
+        self._f64, self._c128 = [], []
+        d = nat.Problem()
+        d.A, d.B, d.F, d.T = plan.A, plan.B, plan.F, plan.T
+        d.n_layers = len(plan.layers)
+        d.backend = BACKENDS[backend]
+        d.prism_inv_n = plan.prism_inv_n
+        slots = [("kx", self._put_f64(plan.kx)), ("k0", self._put_f64(plan.k0)),
+                 ("prism_inv_cos", self._put_f64(plan.prism_inv_cos)),
+                 ("prism_inv_ncos", self._put_f64(plan.prism_inv_ncos))]
+        layer_slots = []
+        for i, lp in enumerate(plan.layers):
+            L = d.layers[i]
+            L.kind = lp.kind
+            L.mu_scalar = 1 if lp.mu_scalar else 0
+            L.iso_eps = nat.c128(lp.iso_eps.real, lp.iso_eps.imag)
+            L.iso_mu = nat.c128(lp.iso_mu.real, lp.iso_mu.imag)
+            L.exit_n = lp.exit_n
+            if lp.eps is not None:
+                L.n_eps, L.n_mu, L.n_beta = lp.eps.shape[0], lp.mu.shape[0], lp.cos_beta.size
+                layer_slots += [(i, "eps", self._put_c128(lp.eps)), (i, "mu", self._put_c128(lp.mu)),
+                                (i, "cos_beta", self._put_f64(lp.cos_beta)), (i, "sin_beta", self._put_f64(lp.sin_beta))]
+            if lp.thickness is not None:
+                L.n_thickness = lp.thickness.size
+                layer_slots.append((i, "thickness", self._put_f64(lp.thickness)))
+            if lp.exit_cos is not None:
+                layer_slots.append((i, "exit_cos", self._put_c128(lp.exit_cos)))
+        f64 = np.concatenate([np.ascontiguousarray(x, dtype=np.float64).reshape(-1) for x in self._f64])
+        c128 = (np.concatenate([np.ascontiguousarray(x, dtype=np.complex128).reshape(-1) for x in self._c128])
+                if self._c128 else np.zeros(1, dtype=np.complex128))
+        self.h2d_bytes = f64.nbytes + c128.nbytes
+        self._f64_dev = torch.from_numpy(f64).to(self.device)
+        self._c128_dev = torch.from_numpy(c128).to(self.device)
+        base_f, base_c = self._f64_dev.data_ptr(), self._c128_dev.data_ptr()
+
+        def addr(slot):
+            kind, offset = slot
+            return (base_f + 8 * offset) if kind == "f" else (base_c + 16 * offset)
+
+        for name, slot in slots:
+            setattr(d, name, addr(slot))
+        for i, name, slot in layer_slots:
+            setattr(d.layers[i], name, addr(slot))
+        self.desc = d
+
+    def _put_f64(self, arr):
+        off = sum(np.size(x) for x in self._f64)
+        self._f64.append(np.asarray(arr))
+        return ("f", off)
+
+    def _put_c128(self, arr):
+        off = sum(np.size(x) for x in self._c128)
+        self._c128.append(np.asarray(arr))
+        return ("c", off)
+
+    @property
+    def n_points(self):
+        return self.plan.n_points
+
+
+class DeviceOutputs:
+    """Caller-owned output buffers for a contiguous range of batch points."""
+
+    def __init__(self, n, device, mueller=True, stokes=None, dtype=torch.complex128):
+        self.n = n
+        self.dtype = dtype
+        real = torch.float64 if dtype == torch.complex128 else torch.float32
+        self.r = torch.empty((4, n), dtype=dtype, device=device)  # rows: pp, ps, sp, ss
+        self.mueller = torch.empty((n, 4, 4), dtype=real, device=device) if mueller else None
+        self.stokes = torch.empty((n, 4), dtype=real, device=device) if stokes is not None else None
+        self.incident_stokes = stokes
+
+    @property
+    def nbytes(self):
+        total = self.r.numel() * self.r.element_size()
+        for t in (self.mueller, self.stokes):
+            if t is not None:
+                total += t.numel() * t.element_size()
+        return total
+
+
+def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None):
+    """Launch the fused kernel for points ``[n_begin, n_end)`` into ``out`` (asynchronous)."""
+    n_end = problem.n_points if n_end is None else n_end
+    if n_end - n_begin > out.n:
+        raise ValueError("output buffers are smaller than the requested point range")
+    handle = (stream or torch.cuda.current_stream(problem.device)).cuda_stream
+    lib = nat.lib()
+    if out.dtype == torch.complex128:
+        o = nat.Outputs()
+        o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
+        o.mueller = out.mueller.data_ptr() if out.mueller is not None else None
+        o.stokes = out.stokes.data_ptr() if out.stokes is not None else None
+        if out.incident_stokes is not None:
+            o.incident_stokes = (C.c_double * 4)(*[float(x) for x in out.incident_stokes])
+        nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
+    else:
+        o = nat.OutputsF32()
+        o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
+        o.mueller = out.mueller.data_ptr() if out.mueller is not None else None
+        nat.check(lib.ho_reflect_f32(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
+
+
+def measure_fp64_peak(iters=1 << 16):
+    """Achieved FP64 FMA FLOP/s of an 8-chain-per-thread FMA loop on the current device."""
+    _require_cuda(None)
+    val = C.c_double(0.0)
+    nat.check(nat.lib().ho_measure_fp64_peak(int(iters), C.byref(val), torch.cuda.current_stream().cuda_stream))
+    return val.value
+
+
+def launch_count():
+    return int(nat.lib().ho_launch_count())

@@ -1,0 +1,197 @@
+"""``Structure`` -- the reference's simulation front door, backed by the CUDA engine.
+
+Mirrors the reference's public protocol (``hyperbolic_optics/structure.py:94-419``):
+
+    s = Structure(); s.execute(payload, backend="transfer" | "scattering")
+    s.r_pp, s.r_ps, s.r_sp, s.r_ss          # complex128, presentation shape (F, A, B, T) squeezed
+
+plus the staged route the reference's tests use (``get_scenario`` -> mutate
+``scenario.incident_angle`` / ``azimuthal_angle`` -> ``setup_attributes`` -> ``get_layers`` ->
+``calculate`` + ``calculate_reflectivity`` | ``calculate_scattering``).  Same payload schema,
+same errors (``ValueError`` for an unknown backend / layer type / second swept thickness,
+``NotImplementedError`` for an unknown scenario or material).  Numerical failure is not an
+error: the transfer backend returns inf/NaN where the reference's 4x4 product overflows.
+
+Additions (all optional): ``mueller`` (the sample Mueller matrix, fused into the same
+kernel), ``stokes`` for a given incident Stokes vector, ``device=`` / ``keep_on_device=``.
+
+What is *not* materialised: per-layer 4x4 matrices, eigenvector profiles and
+``transfer_matrix`` -- the kernel keeps a 4x2 plane in registers instead,
+so ``transfer_matrix`` stays ``None`` and ``layers[i].matrix`` does not exist.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine
+from .plan import StackPlan, build_plan
+from .scenario import ScenarioSetup, present
+
+_PINNED_POOL = {}
+
+
+def _pinned(name, shape, dtype):
+    """Reusable pinned host buffers (allocation of GBs of page-locked memory is slow)."""
+    key = (name, tuple(shape), dtype)
+    buf = _PINNED_POOL.get(key)
+    if buf is None:
+        for k in [k for k in _PINNED_POOL if k[0] == name]:
+            del _PINNED_POOL[k]
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+        _PINNED_POOL[key] = buf
+    return buf
+
+
+class Structure:
+    """Drop-in for ``hyperbolic_optics.structure.Structure`` on one B200."""
+
+    def __init__(self, device=None, chunk_points=1 << 22):
+        self.scenario = None
+        self.layers = []
+        self.incident_angle = None
+        self.azimuthal_angle = None
+        self.frequency = None
+        self.eps_prism = None
+        self.k_x = None
+        self.k_0 = None
+        self.r_pp = self.r_ss = self.r_ps = self.r_sp = None
+        self.t_pp = self.t_ss = self.t_ps = self.t_sp = None
+        self.transfer_matrix = None
+        self.mueller = None
+        self.stokes = None
+        self.plan: StackPlan | None = None
+        self.device = device
+        self.chunk_points = int(chunk_points)
+        self.with_mueller = True
+        self.incident_stokes = None
+        self.keep_on_device = False
+        # True: results are private NumPy copies (drop-in semantics).  False: zero-copy views of
+        # the reusable pinned staging buffers, valid until the next run of the same shape.
+        self.own_results = True
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._backend = "transfer"
+
+    # -- staged protocol ---------------------------------------------------------------
+    def get_scenario(self, scenario_data):
+        self.scenario = ScenarioSetup(scenario_data)
+        self.setup_attributes()
+
+    def setup_attributes(self):
+        self.incident_angle = self.scenario.incident_angle
+        self.azimuthal_angle = self.scenario.azimuthal_angle
+        self.frequency = self.scenario.frequency
+
+    def get_layers(self, layer_data_list):
+        """Host planning: resolves frequency, kx/k0 and per-layer tables (no device work)."""
+        self.plan = build_plan(self.scenario, layer_data_list)
+        self.layers = [_PrismRecord(self.plan)] + list(self.plan.layers)
+        self.eps_prism = self.plan.eps_prism
+        self.frequency = self.plan.frequency
+        self.k_x = self.plan.kx.reshape(-1, 1, 1, 1)
+        self.k_0 = self.plan.k0.reshape(1, 1, -1, 1)
+
+    def calculate(self):
+        """Transfer backend selected; the product itself is fused into the kernel launch."""
+        self._backend = "transfer"
+
+    def calculate_reflectivity(self):
+        self._run(self._backend)
+
+    def calculate_scattering(self):
+        self._run("scattering")
+
+    def calculate_transmissivity(self):
+        raise NotImplementedError(
+            "t_* for the GPU engine is not available yet (needs LAPACK-convention eigenvectors "
+            "for a crystal exit; see DESIGN.md 'next').")
+
+    # -- one-call protocol ---------------------------------------------------------------
+    def execute(self, payload, backend="transfer", mueller=True, incident_stokes=None,
+                keep_on_device=False, own_results=None):
+        if backend not in ("transfer", "scattering"):
+            raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
+        self.with_mueller = bool(mueller)
+        self.incident_stokes = incident_stokes
+        self.keep_on_device = bool(keep_on_device)
+        if own_results is not None:
+            self.own_results = bool(own_results)
+        self.get_scenario(payload.get("ScenarioData"))
+        self.get_layers(payload.get("Layers", None))
+        self._run(backend)
+
+    # -- device run ------------------------------------------------------------------------
+    def _run(self, backend):
+        plan = self.plan
+        prob = engine.DeviceProblem(plan, backend, self.device)
+        self.h2d_bytes = prob.h2d_bytes
+        n = plan.n_points
+        shape = plan.fabt_shape
+        want_stokes = self.incident_stokes is not None
+        if self.keep_on_device:
+            out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes)
+            engine.reflect(prob, out)
+            r = out.r.reshape((4,) + shape)
+            self._assign(r, out.mueller, out.stokes, shape, to_numpy=False)
+            self.d2h_bytes = 0
+            return
+        # host results: kernel -> device chunk (double buffered) -> pinned host, D2H on a copy stream
+        chunk = min(n, self.chunk_points)
+        host_r = _pinned("r", (4, n), torch.complex128)
+        host_m = _pinned("m", (n, 4, 4), torch.float64) if self.with_mueller else None
+        host_s = _pinned("s", (n, 4), torch.float64) if want_stokes else None
+        bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes)
+                for _ in range(2 if n > chunk else 1)]
+        compute = torch.cuda.current_stream(prob.device)
+        copy = torch.cuda.Stream(prob.device)
+        done = [None] * len(bufs)
+        for ci, start in enumerate(range(0, n, chunk)):
+            stop = min(n, start + chunk)
+            buf = bufs[ci % len(bufs)]
+            if done[ci % len(bufs)] is not None:
+                compute.wait_event(done[ci % len(bufs)])  # previous D2H out of this buffer finished
+            engine.reflect(prob, buf, start, stop, stream=compute)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            copy.wait_event(ready)
+            with torch.cuda.stream(copy):
+                m = stop - start
+                for i in range(4):  # contiguous row slices -> plain cudaMemcpyAsync each
+                    host_r[i, start:stop].copy_(buf.r[i, :m], non_blocking=True)
+                if host_m is not None:
+                    host_m[start:stop].copy_(buf.mueller[:m], non_blocking=True)
+                if host_s is not None:
+                    host_s[start:stop].copy_(buf.stokes[:m], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            done[ci % len(bufs)] = ev
+        copy.synchronize()
+        self.d2h_bytes = n * (64 + (128 if host_m is not None else 0) + (32 if host_s is not None else 0))
+        self._assign(host_r.reshape((4,) + shape), host_m, host_s, shape, to_numpy=True)
+
+    def _assign(self, r, mueller, stokes, shape, to_numpy):
+        if to_numpy:
+            conv = (lambda t: np.array(t.numpy())) if self.own_results else (lambda t: t.numpy())
+        else:
+            conv = lambda t: t
+        pres = present if to_numpy else _present_torch
+        self.r_pp, self.r_ps, self.r_sp, self.r_ss = (pres(conv(r[i])) for i in range(4))
+        self.mueller = pres(conv(mueller.reshape(shape + (4, 4)))) if mueller is not None else None
+        self.stokes = pres(conv(stokes.reshape(shape + (4,)))) if stokes is not None else None
+
+
+def _present_torch(t):
+    lead = tuple(n for n in t.shape[:4] if n != 1)
+    return t.reshape(lead + tuple(t.shape[4:]))
+
+
+class _PrismRecord:
+    """Layer-list entry for the incident medium (reference ``layers.py:432-460``)."""
+
+    type = "Ambient Incident Layer"
+    thickness = None
+
+    def __init__(self, plan):
+        self.eps_prism = plan.eps_prism

@@ -1,0 +1,131 @@
+/*
+ * ho_b200.h -- C ABI of the B200-native Berreman reflection engine (libho_b200.so).
+ *
+ * The reference (hyperbolic-optics 0.3.0) is pure Python/NumPy and has no FFI of its own;
+ * the seam this library sits behind is the Python object protocol of
+ *   Structure.execute(payload, backend)                    reference structure.py:370-419
+ * Each entry point below names the reference call it replaces.  Host code (Python, via
+ * ctypes -- see INTEGRATION.md) builds the small per-axis tables exactly like the
+ * reference's layer constructors do and hands the O(A*B*F*T) work to one fused kernel.
+ *
+ * Conventions
+ *   - complex numbers are interleaved (re, im) doubles (ho_c128) or floats;
+ *   - batch point index n = ((f*A + a)*B + b)*T + t, i.e. the reference's presentation
+ *     order (F, A, B, T) of axes.py:83-95, so every output is already "presented";
+ *   - all pointers in ho_problem_t / ho_outputs_t are DEVICE pointers owned by the caller
+ *     (PyTorch tensors used as plain buffers); the library never allocates outputs;
+ *   - functions return 0 on success or a negative ho_status; ho_last_error() gives text.
+ *     Numerical failure is not an error: inf/NaN flow into the outputs like the reference
+ *     (tests/test_scattering.py:86-91 of the reference require exactly that).
+ */
+#ifndef HO_B200_H
+#define HO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HO_ABI_VERSION 1
+#define HO_MAX_LAYERS 24
+
+typedef struct { double re, im; } ho_c128;
+
+enum ho_status {
+  HO_OK = 0,
+  HO_ERR_BAD_ARGUMENT = -1, /* malformed descriptor (layer order, sizes, null tables) */
+  HO_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  HO_ERR_NO_DEVICE = -3
+};
+
+/* layer kinds below the prism, top to bottom (reference layers.py:669-683 factory keys) */
+enum ho_layer_kind {
+  HO_ISO_FILM = 1,   /* "Isotropic Middle-Stack Layer"      layers.py:463-540 */
+  HO_ANISO_FILM = 2, /* "Crystal Layer"                     layers.py:543-579 */
+  HO_ANISO_EXIT = 3, /* "Semi Infinite Anisotropic Layer"   layers.py:582-617 */
+  HO_ISO_EXIT = 4    /* "Semi Infinite Isotropic Layer"     layers.py:620-666 */
+};
+
+/* backends of Structure.execute(payload, backend=...)        structure.py:395-410 */
+enum ho_backend {
+  HO_BACKEND_TRANSFER = 0,  /* ordered 4x4 product semantics (overflows like the reference) */
+  HO_BACKEND_SCATTERING = 1 /* stable recursion, only decaying exponentials (scattering.py) */
+};
+
+typedef struct {
+  int32_t kind;        /* ho_layer_kind */
+  int32_t n_eps;       /* rows of eps table: 1 (constant) or F */
+  int32_t n_mu;        /* rows of mu table: 1 or F */
+  int32_t mu_scalar;   /* 1: mu = mu[.,0] * I (rotation invariant)  0: full symmetric tensor */
+  int32_t n_beta;      /* entries of cos_beta/sin_beta: 1 or B */
+  int32_t n_thickness; /* entries of thickness: 1 or T (0 for semi-infinite layers) */
+  /* packed symmetric tensors (xx,xy,xz,yy,yz,zz) per frequency, already rotated by
+     Ry(rotY+1e-8)*Rx(rotX) on the host (layers.py:26-66,283); [n_eps][6], [n_mu][6] */
+  const ho_c128* eps;
+  const ho_c128* mu;
+  /* z rotation beta = azimuth[b] + rotZ + 1e-9 (layers.py:284,318-351) as cos/sin tables */
+  const double* cos_beta;
+  const double* sin_beta;
+  const double* thickness; /* cm (layers.py:301-308) */
+  ho_c128 iso_eps, iso_mu; /* HO_ISO_FILM scalars (layers.py:484-523) */
+  const ho_c128* exit_cos; /* HO_ISO_EXIT: cos(theta_f)[A], complex principal root (layers.py:190-238) */
+  double exit_n;           /* HO_ISO_EXIT: sqrt(eps_exit) */
+} ho_layer_t;
+
+typedef struct {
+  int32_t A, B, F, T;            /* canonical batch sizes (axes.py:21) */
+  int32_t n_layers;              /* layers below the prism, <= HO_MAX_LAYERS */
+  int32_t backend;               /* ho_backend */
+  const double* kx;              /* [A] sqrt(eps_prism) sin(theta)       structure.py:183 */
+  const double* k0;              /* [F] 2 pi f                           structure.py:189 */
+  const double* prism_inv_cos;   /* [A] 1/cos(theta)                     layers.py:109-152 */
+  const double* prism_inv_ncos;  /* [A] 1/(n cos(theta)) */
+  double prism_inv_n;            /* 1/n */
+  ho_layer_t layers[HO_MAX_LAYERS];
+} ho_problem_t;
+
+typedef struct {
+  /* each [n_end - n_begin] complex128, presentation order; replaces structure.r_pp ...
+     (structure.py:272-314 / scattering.py:155-164).  Any pointer may be NULL to skip. */
+  ho_c128* r_pp;
+  ho_c128* r_ps;
+  ho_c128* r_sp;
+  ho_c128* r_ss;
+  /* [n][16] float64 row-major Mueller matrix M = Re(A F A^-1)   mueller.py:256-325 */
+  double* mueller;
+  /* [n][4] Stokes vector M * incident_stokes (mueller.py:479-500); needs mueller math only */
+  double* stokes;
+  double incident_stokes[4];
+} ho_outputs_t;
+
+/* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /
+   calculate_scattering) for batch points [n_begin, n_end) of the presentation-ordered grid.
+   Output pointers address element 0 of that range.  `cuda_stream` is a cudaStream_t (or NULL
+   for the default stream).  Asynchronous: returns after the launch. */
+int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out,
+               int64_t n_begin, int64_t n_end, void* cuda_stream);
+
+/* Same computation in complex64 arithmetic (opt-in; tolerance 1e-4).  Tables stay float64 /
+   complex128; outputs are complex64 (interleaved floats) and float32. */
+typedef struct {
+  float* r_pp; float* r_ps; float* r_sp; float* r_ss; /* interleaved (re, im) */
+  float* mueller;                                    /* [n][16] */
+} ho_outputs_f32_t;
+int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out,
+                   int64_t n_begin, int64_t n_end, void* cuda_stream);
+
+/* FP64 FMA-chain microbenchmark used as the roofline denominator: runs `iters` dependent
+   FMA rounds on every SM and returns achieved FLOP/s (2 flops per FMA) in *flops_per_s. */
+int ho_measure_fp64_peak(int iters, double* flops_per_s, void* cuda_stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t ho_launch_count(void);
+
+int ho_abi_version(void);
+const char* ho_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HO_B200_H */

@@ -1,0 +1,156 @@
+"""Host-side logic (CPU): scenario grids, material tables, planner, error contract, and the
+C-ABI library (loads, exports every symbol include/ho_b200.h declares -- no compute calls)."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from hyperbolic_optics_b200 import materials, plan as planmod
+from hyperbolic_optics_b200.scenario import ScenarioSetup, present
+from oracle import reference_port as oracle
+from tests.golden.payloads import ALL, REFERENCE_BATTERY, angle_overrides
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("kind,sd", [
+    ("Incident", {"type": "Incident"}),
+    ("Azimuthal", {"type": "Azimuthal", "incidentAngle": 40}),
+    ("Dispersion", {"type": "Dispersion", "frequency": 1460.0}),
+    ("FullSweep", {"type": "FullSweep"}),
+    ("Simple", {"type": "Simple", "incidentAngle": 45.0, "azimuthal_angle": 10.0, "frequency": 1460.0}),
+])
+def test_scenario_grids_equal_reference_port(kind, sd):
+    sc = ScenarioSetup(sd)
+    inc, az, freq = oracle.scenario_grids(sd)
+    np.testing.assert_array_equal(np.asarray(sc.incident_angle), np.asarray(inc))
+    if az is not None:
+        np.testing.assert_array_equal(np.asarray(sc.azimuthal_angle), np.asarray(az))
+    assert sc.frequency == freq
+
+
+def test_default_shapes():
+    assert ScenarioSetup({"type": "Incident"}).incident_angle.shape == (360,)
+    sc = ScenarioSetup({"type": "Dispersion", "frequency": 900.0})
+    assert sc.incident_angle.shape == (180,) and sc.azimuthal_angle.shape == (480,)
+    sc = ScenarioSetup({"type": "FullSweep"})
+    assert sc.incident_angle.shape == (180,) and sc.azimuthal_angle.shape == (120,)
+    assert ScenarioSetup({"type": "Incident"}, n_incident=4096).incident_angle.shape == (4096,)
+
+
+@pytest.mark.parametrize("name", ["Quartz", "Sapphire", "Calcite", "CalciteLower", "AlN", "SiC", "hBN", "GaN",
+                                  "MoO3", "GalliumOxide"])
+def test_material_tables_equal_oracle(name):
+    mat = materials.create_material(name)
+    freq = mat.frequency
+    assert freq.shape == (410,)
+    np.testing.assert_array_equal(freq, oracle.default_frequency(name))
+    eps_ref, mu_ref = oracle.material_tensors(name, freq)
+    np.testing.assert_allclose(materials.unpack_symmetric(mat.eps_packed(freq)), eps_ref, rtol=1e-15, atol=0)
+    np.testing.assert_array_equal(materials.unpack_symmetric(mat.mu_packed(freq))[0], mu_ref[0])
+
+
+def test_arbitrary_material():
+    spec = {"eps_xx": {"real": 2.27, "imag": 0.001}, "eps_yy": -4.84, "eps_zz": "1+2j", "eps_xy": 0.3, "mu_r": 2.0}
+    mat = materials.create_material(spec)
+    assert mat.frequency is None
+    eps_ref, mu_ref = oracle.material_tensors(spec, [1000.0])
+    np.testing.assert_array_equal(materials.unpack_symmetric(mat.eps_packed([1000.0]))[0], eps_ref)
+    np.testing.assert_array_equal(materials.unpack_symmetric(mat.mu_packed([1000.0]))[0], mu_ref)
+
+
+def test_error_contract():
+    with pytest.raises(NotImplementedError):
+        materials.create_material("Unobtainium")
+    with pytest.raises(NotImplementedError):
+        ScenarioSetup({"type": "Nope"})
+    sc = ScenarioSetup({"type": "Incident"})
+    with pytest.raises(ValueError):
+        planmod.build_plan(sc, [{"type": "Ambient Incident Layer", "permittivity": 5.0}, {"type": "Bogus Layer"}])
+    two_swept = [{"type": "Ambient Incident Layer", "permittivity": 5.0},
+                 {"type": "Isotropic Middle-Stack Layer", "thickness": [0.1, 0.2]},
+                 {"type": "Crystal Layer", "material": "Quartz", "thickness": [0.1, 0.2]},
+                 {"type": "Semi Infinite Anisotropic Layer", "material": "Quartz"}]
+    with pytest.raises(ValueError):
+        planmod.build_plan(ScenarioSetup({"type": "Incident"}), two_swept)
+    with pytest.raises(ValueError):
+        planmod.build_plan(ScenarioSetup({"type": "Incident"}),
+                           [{"type": "Ambient Incident Layer", "permittivity": 5.0},
+                            {"type": "Semi Infinite Isotropic Layer", "permittivity": 1.0}])  # no frequency
+
+
+@pytest.mark.parametrize("name", list(ALL))
+def test_plan_tables_match_oracle_stack(name):
+    """kx, k0, prism scalings, rotated tensors and thickness of the planner == the port's arrays."""
+    entry = ALL[name]
+    inc, az = angle_overrides(entry)
+    sc = ScenarioSetup(entry["payload"]["ScenarioData"])
+    if inc is not None:
+        sc.incident_angle = inc
+    if az is not None:
+        sc.azimuthal_angle = az
+    plan = planmod.build_plan(sc, entry["payload"]["Layers"])
+    with np.errstate(all="ignore"):
+        st = oracle.build_stack(entry["payload"], inc, az)
+    np.testing.assert_array_equal(plan.kx, st["kx"].reshape(-1))
+    np.testing.assert_array_equal(plan.k0, st["k0"].reshape(-1))
+    prism = st["layers"][0].matrix.reshape(-1, 4, 4)
+    np.testing.assert_allclose(0.5 * plan.prism_inv_cos, prism[:, 2, 0].real, rtol=1e-15)
+    np.testing.assert_allclose(0.5 * plan.prism_inv_ncos, prism[:, 1, 2].real, rtol=1e-15)
+    assert plan.n_points == int(np.prod([plan.A, plan.B, plan.F, plan.T]))
+    for lp, ref in zip(plan.layers, st["layers"][1:]):
+        assert lp.type == ref.kind
+        if lp.thickness is not None:
+            np.testing.assert_allclose(lp.thickness, np.asarray(ref.thickness).reshape(-1), rtol=1e-15)
+        if lp.kind == planmod.KIND_ISO_EXIT:
+            np.testing.assert_allclose(lp.exit_cos, ref.matrix.reshape(-1, 4, 4)[:, 0, 2], rtol=1e-15)
+
+
+def test_present_squeezes_like_reference():
+    x = np.arange(2 * 3 * 1 * 1).reshape(2, 3, 1, 1)
+    assert present(x).shape == (2, 3)
+    assert present(np.zeros((1, 1, 1, 1))).shape == ()
+    assert present(np.zeros((5, 1, 4, 1, 4, 4))).shape == (5, 4, 4, 4)
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    header = (ROOT / "include" / "ho_b200.h").read_text()
+    declared = set(re.findall(r"\b(ho_[a-z0-9_]+)\s*\(", header))
+    assert {"ho_reflect", "ho_reflect_f32", "ho_measure_fp64_peak", "ho_launch_count", "ho_abi_version",
+            "ho_last_error"} <= declared
+    for sym in declared:
+        assert hasattr(built_library, sym), f"{sym} declared in ho_b200.h but not exported"
+    assert built_library.ho_abi_version() == 1
+    assert built_library.ho_launch_count() == 0
+
+
+def test_descriptor_validation_without_gpu(built_library):
+    """Bad descriptors are rejected on the host before any CUDA call."""
+    from hyperbolic_optics_b200 import _native as nat
+
+    prob = nat.Problem()
+    out = nat.Outputs()
+    rc = built_library.ho_reflect(ctypes.byref(prob), ctypes.byref(out), 0, 0, None)
+    assert rc == -1 and b"batch sizes" in built_library.ho_last_error()
+    prob.A = prob.B = prob.F = prob.T = 1
+    prob.n_layers = 99
+    assert built_library.ho_reflect(ctypes.byref(prob), ctypes.byref(out), 0, 0, None) == -1
+
+
+def test_struct_layout_matches_header():
+    from hyperbolic_optics_b200 import _native as nat
+
+    assert ctypes.sizeof(nat.LayerDesc) == 112
+    assert ctypes.sizeof(nat.Problem) == 64 + 24 * 112
+    assert nat.Problem.layers.offset == 64
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: no product module may reference it."""
+    for path in (ROOT / "hyperbolic_optics_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "oracle" not in text.replace("# oracle", ""), f"{path} mentions the oracle"
+        assert "tools." not in text and "from tools" not in text
