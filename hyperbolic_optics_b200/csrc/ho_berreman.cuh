@@ -13,7 +13,9 @@ namespace ho {
 
 // Berreman matrix for symmetric eps, mu (reference waves.py:221-245):
 //   [[a, b, c, d], [0, e, f, -c], [g, h, e, -b], [j, -g, 0, a]]
-template <typename T> struct Delta { cx<T> a, b, c, d, e, f, g, h, j; };
+// NM = true: mu is a scalar multiple of the identity, so c = e = 0 (and f = -mu); the members
+// stay in the struct but are never read, which lets the compiler drop them.
+template <typename T, bool NM = false> struct Delta { cx<T> a, b, c, d, e, f, g, h, j; };
 template <typename T> struct Vec4 { cx<T> v0, v1, v2, v3; };
 template <typename T> struct Sym6 { cx<T> xx, xy, xz, yy, yz, zz; };
 // sums / products of the forward and backward root pairs
@@ -54,6 +56,23 @@ template <typename T> __device__ __forceinline__ Sym6<T> rotate_z(const Sym6<T>&
   return r;
 }
 
+// scalar-mu flavour: m = mu * I
+template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k, const Sym6<T>& e, cx<T> mu) {
+  cx<T> ie = recip(e.zz), im = recip(mu);
+  T k2 = k * k;
+  Delta<T, true> D;
+  D.a = -(k * (e.xz * ie));
+  D.b = -(k * (e.yz * ie));
+  D.d = mu - k2 * ie;
+  D.f = -mu;
+  D.g = e.yz * e.xz * ie - e.xy;
+  D.h = k2 * im - e.yy + e.yz * e.yz * ie;
+  D.j = e.xx - e.xz * e.xz * ie;
+  D.c = mk<T>(T(0), T(0));
+  D.e = mk<T>(T(0), T(0));
+  return D;
+}
+
 template <typename T> __device__ __forceinline__ Delta<T> berreman(T k, const Sym6<T>& e, const Sym6<T>& m) {
   cx<T> ie = recip(e.zz), im = recip(m.zz);
   T k2 = k * k;
@@ -70,6 +89,15 @@ template <typename T> __device__ __forceinline__ Delta<T> berreman(T k, const Sy
   return D;
 }
 
+template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T, true>& D, const Vec4<T>& v) {
+  Vec4<T> r;
+  r.v0 = fma(D.d, v.v3, fma(D.b, v.v1, D.a * v.v0));
+  r.v1 = D.f * v.v2;
+  r.v2 = fma(D.h, v.v1, D.g * v.v0) - D.b * v.v3;
+  r.v3 = fma(D.a, v.v3, D.j * v.v0) - D.g * v.v1;
+  return r;
+}
+
 template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T>& D, const Vec4<T>& v) {
   Vec4<T> r;
   r.v0 = fma(D.d, v.v3, fma(D.c, v.v2, fma(D.b, v.v1, D.a * v.v0)));
@@ -80,6 +108,14 @@ template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T>& 
 }
 
 // det(lambda I - D) = lambda^4 + c3 lambda^3 + c2 lambda^2 + c1 lambda + c0
+template <typename T> __device__ __forceinline__ void charpoly(const Delta<T, true>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
+  cx<T> a2 = D.a * D.a, ab = D.a * D.b;
+  c3 = T(-2) * D.a;
+  c2 = a2 - D.d * D.j - D.f * D.h;
+  c1 = T(2) * (D.f * (D.a * D.h - D.b * D.g));
+  c0 = D.f * (T(2) * (ab * D.g) - a2 * D.h + D.b * D.b * D.j + D.d * (D.g * D.g + D.h * D.j));
+}
+
 template <typename T> __device__ __forceinline__ void charpoly(const Delta<T>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
   cx<T> a2 = D.a * D.a, e2 = D.e * D.e, cg = D.c * D.g, dj = D.d * D.j, fh = D.f * D.h;
   cx<T> bcj = D.b * D.c * D.j, bf = D.b * D.f, ae = D.a * D.e;
@@ -135,6 +171,41 @@ template <typename T> __device__ __forceinline__ void ferrari(cx<T> c3, cx<T> c2
   lam[0] = y0 - q3; lam[1] = y1 - q3; lam[2] = y2 - q3; lam[3] = y3 - q3;
 }
 
+// Start values for the spectral split.  The closed form only has to be good enough to classify
+// the roots and to land inside Bairstow's basin, so it runs in FP32 (on the FP32 pipe, next to the
+// FP64 work of neighbouring warps); one guarded Newton step per root in working precision then
+// restores ~1e-12 accuracy before the forward/backward classification.
+__device__ __forceinline__ void start_roots(cx<float> c3, cx<float> c2, cx<float> c1, cx<float> c0, cx<float> lam[4]) {
+  // scale the roots to O(1) so the resolvent's sixth powers stay inside the FP32 range
+  float sc = fmaxf(fmaxf(cabs(c3), sqrtf(cabs(c2))), fmaxf(cbrtf(cabs(c1)), sqrtf(sqrtf(cabs(c0)))));
+  if (!(sc > 0.f) || !(sc < 3.0e38f)) sc = 1.f;
+  float is = 1.f / sc, is2 = is * is;
+  ferrari(is * c3, is2 * c2, (is2 * is) * c1, (is2 * is2) * c0, lam);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) lam[i] = sc * lam[i];
+}
+__device__ __forceinline__ void start_roots(cx<double> c3, cx<double> c2, cx<double> c1, cx<double> c0, cx<double> lam[4]) {
+#ifdef HO_FERRARI_FP64
+  ferrari(c3, c2, c1, c0, lam);
+#else
+  cx<float> l32[4];
+  start_roots(mk<float>((float)c3.re, (float)c3.im), mk<float>((float)c2.re, (float)c2.im),
+              mk<float>((float)c1.re, (float)c1.im), mk<float>((float)c0.re, (float)c0.im), l32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    cx<double> x = mk<double>((double)l32[i].re, (double)l32[i].im);
+    cx<double> pv = fma(fma(fma(x + c3, x, c2), x, c1), x, c0);
+    cx<double> dv = fma(fma(4.0 * x + 3.0 * c3, x, 2.0 * c2), x, c1);
+    double dn = norm2(dv);
+    if (dn > 0.0) {
+      cx<double> step = pv * mk<double>(dv.re / dn, -dv.im / dn);
+      if (norm2(step) <= 0.25 * norm2(x)) x = x - step;
+    }
+    lam[i] = x;
+  }
+#endif
+}
+
 // Forward ("transmitted") pair selection, reference waves.py:273-289: all |Im| > 1e-9 -> two
 // largest Im; none -> two largest Re; mixed -> Im > tol, or |Im| <= tol and Re > 0 (ranked).
 template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4], bool fwd[4]) {
@@ -168,11 +239,11 @@ template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4
 
 // Newton (Bairstow) on the quadratic factor lambda^2 + u lambda + v of the quartic; the
 // complementary factor lambda^2 + b1 lambda + b0 follows by deflation.
-template <typename T> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T>& D) {
+template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D) {
   cx<T> c3, c2, c1, c0;
   charpoly(D, c3, c2, c1, c0);
   cx<T> lam[4];
-  ferrari(c3, c2, c1, c0, lam);
+  start_roots(c3, c2, c1, c0, lam);
   bool fwd[4];
   classify(lam, fwd);
   cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
@@ -216,7 +287,7 @@ template <typename T> __device__ __forceinline__ void projector_coeffs(const Spe
 }
 
 // z = P_f y, also returns dy = D y
-template <typename T> __device__ __forceinline__ Vec4<T> project_forward(const Delta<T>& D, const Spectrum<T>& s, cx<T> h0, cx<T> h1,
+template <typename T, bool NM> __device__ __forceinline__ Vec4<T> project_forward(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> h0, cx<T> h1,
                                                                         const Vec4<T>& y, Vec4<T>& dy) {
   dy = matvec(D, y);
   Vec4<T> w = axpy(h1, dy, scale(h0, y));
@@ -268,7 +339,7 @@ template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> s, c
 }
 
 // exp(c D) Y, unnormalised (transfer-matrix semantics: overflows for thick evanescent layers)
-template <typename T> __device__ __forceinline__ void film_transfer(const Delta<T>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
+template <typename T, bool NM> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   Vec4<T> dy0, dy1;
@@ -295,7 +366,7 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 
 // Stable propagation of the plane span(Y) through a film: only decaying exponentials.
 // Renormalises so that rows (Ex, Ey) of the forward part are the identity.
-template <typename T> __device__ __forceinline__ void film_stable(const Delta<T>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
+template <typename T, bool NM> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   Vec4<T> dy;
@@ -320,16 +391,21 @@ template <typename T> __device__ __forceinline__ void film_stable(const Delta<T>
   y1 = axpy(g1.v1, e1, axpy(g1.v0, e0, xf1));
 }
 
-// Forward invariant subspace of a semi-infinite crystal: P_f [e0 e1]
-template <typename T> __device__ __forceinline__ void substrate_plane(const Delta<T>& D, const Spectrum<T>& s, Vec4<T>& y0, Vec4<T>& y1) {
+// Forward invariant subspace of a semi-infinite crystal: P_f [e0 e1].  With unit seeds the first
+// product D e_k is just a column of D, so each column costs two mat-vecs instead of three.
+template <typename T, bool NM> __device__ __forceinline__ void substrate_plane(const Delta<T, NM>& D, const Spectrum<T>& s, Vec4<T>& y0, Vec4<T>& y1) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
-  const cx<T> one = mk<T>(T(1), T(0)), zero = mk<T>(T(0), T(0));
-  Vec4<T> e0, e1, dy;
-  e0.v0 = one; e0.v1 = zero; e0.v2 = zero; e0.v3 = zero;
-  e1.v0 = zero; e1.v1 = one; e1.v2 = zero; e1.v3 = zero;
-  y0 = project_forward(D, s, h0, h1, e0, dy);
-  y1 = project_forward(D, s, h0, h1, e1, dy);
+  const cx<T> zero = mk<T>(T(0), T(0));
+  Vec4<T> w;
+  // column 0 of D is (a, 0, g, j)
+  w.v0 = fma(h1, D.a, h0); w.v1 = zero; w.v2 = h1 * D.g; w.v3 = h1 * D.j;
+  Vec4<T> t1 = matvec(D, w);
+  y0 = axpy(s.pb, w, axpy(-s.sb, t1, matvec(D, t1)));
+  // column 1 of D is (b, e, h, -g)
+  w.v0 = h1 * D.b; w.v1 = NM ? h0 : fma(h1, D.e, h0); w.v2 = h1 * D.h; w.v3 = -(h1 * D.g);
+  t1 = matvec(D, w);
+  y1 = axpy(s.pb, w, axpy(-s.sb, t1, matvec(D, t1)));
 }
 
 // ---- isotropic layers: D^2 = kz^2 I, closed forms (reference-equivalent) ----

@@ -45,18 +45,28 @@ template <typename T> __device__ __forceinline__ ho::Sym6<T> load_sym(const ho_c
   return s;
 }
 
-template <typename T> __device__ __forceinline__ ho::Delta<T> layer_delta(const ho_layer_t& L, T k, int f, int b) {
+template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer_delta(const ho_layer_t& L, T k, int f, int b) {
   using namespace ho;
   int bi = L.n_beta > 1 ? b : 0;
   T cb = T(__ldg(L.cos_beta + bi)), sb = T(__ldg(L.sin_beta + bi));
   Sym6<T> e = rotate_z(load_sym<T>(L.eps, L.n_eps > 1 ? f : 0), cb, sb);
-  Sym6<T> m = load_sym<T>(L.mu, L.n_mu > 1 ? f : 0);
-  if (!L.mu_scalar) m = rotate_z(m, cb, sb);
-  return berreman(k, e, m);
+  if constexpr (NM) {
+    return berreman_nm(k, e, ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0)));
+  } else {
+    Sym6<T> m = load_sym<T>(L.mu, L.n_mu > 1 ? f : 0);
+    if (!L.mu_scalar) m = rotate_z(m, cb, sb);
+    return berreman(k, e, m);
+  }
 }
 
-template <typename T, bool STABLE>
-__global__ void __launch_bounds__(kThreads)
+#ifndef HO_MIN_BLOCKS
+#define HO_MIN_BLOCKS 2
+#endif
+
+// NM: every crystal layer of the stack has mu proportional to the identity (all built-in
+// materials) -> sparser Berreman matrix; the general kernel handles full mu tensors.
+template <typename T, bool STABLE, bool NM>
+__global__ void __launch_bounds__(kThreads, HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end) {
   using namespace ho;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -77,7 +87,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
       if (L.kind == HO_ISO_EXIT) {
         exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
       } else if (L.kind == HO_ANISO_EXIT) {
-        Delta<T> D = layer_delta<T>(L, k, f, b);
+        Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
         Spectrum<T> s = split_spectrum(D);
         substrate_plane(D, s, y0, y1);
       } else {
@@ -86,7 +96,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
         if (L.kind == HO_ISO_FILM) {
           iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1);
         } else {
-          Delta<T> D = layer_delta<T>(L, k, f, b);
+          Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
           Spectrum<T> s = split_spectrum(D);
           if (STABLE) film_stable(D, s, c, y0, y1);
           else film_transfer(D, s, c, y0, y1);
@@ -187,12 +197,22 @@ int grid_for(int64_t n, const void* kernel) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+template <typename T, bool STABLE, bool NM>
+int launch_nm(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
+  const void* kern = (const void*)reflect_kernel<T, STABLE, NM>;
+  int grid = grid_for(n_end - n_begin, kern);
+  reflect_kernel<T, STABLE, NM><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end);
+  return 0;
+}
+
 template <typename T, bool STABLE>
 int launch(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
   if (n_end == n_begin) return HO_OK;
-  const void* kern = (const void*)reflect_kernel<T, STABLE>;
-  int grid = grid_for(n_end - n_begin, kern);
-  reflect_kernel<T, STABLE><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end);
+  bool nm = true;
+  for (int l = 0; l < p->n_layers; ++l)
+    if ((p->layers[l].kind == HO_ANISO_FILM || p->layers[l].kind == HO_ANISO_EXIT) && !p->layers[l].mu_scalar) nm = false;
+  if (nm) launch_nm<T, STABLE, true>(p, out, n_begin, n_end, stream);
+  else launch_nm<T, STABLE, false>(p, out, n_begin, n_end, stream);
   g_launches.fetch_add(1);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(HO_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
