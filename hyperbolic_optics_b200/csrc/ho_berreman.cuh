@@ -237,8 +237,44 @@ template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4
   }
 }
 
-// Newton (Bairstow) on the quadratic factor lambda^2 + u lambda + v of the quartic; the
+// Bairstow: Newton on (u, v) so that lambda^2 + u lambda + v divides the quartic; the
 // complementary factor lambda^2 + b1 lambda + b0 follows by deflation.
+template <typename T> __device__ __forceinline__ void bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0) {
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    b1 = c3 - u;
+    b0 = c2 - u * b1 - v;
+    cx<T> r1 = c1 - u * b0 - v * b1;
+    cx<T> r0 = c0 - v * b0;
+    cx<T> umb = u - b1;
+    cx<T> j22 = v - b0;
+    cx<T> j11 = j22 - u * umb;
+    cx<T> j21 = -(v * umb);
+    cx<T> det = j11 * j22 - umb * j21;
+    if (norm2(det) > T(0)) {
+      cx<T> idet = recip(det);
+      u = u + (r0 * umb - r1 * j22) * idet;
+      v = v + (r1 * j21 - r0 * j11) * idet;
+    }
+  }
+  b1 = c3 - u;
+  b0 = c2 - u * b1 - v;
+}
+
+// Roots m +- h of lambda^2 + u lambda + v for classification: a pair closer than sqrt(tau)
+// (relative) counts as a double root at m, so rounding noise in h cannot flip its side.
+template <typename T> __device__ __forceinline__ void pair_roots(cx<T> u, cx<T> v, cx<T>& ra, cx<T>& rb) {
+  const T tau = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
+  cx<T> m = T(-0.5) * u;
+  cx<T> h = csqrt(m * m - v);
+  if (norm2(h) <= tau * norm2(m)) h = mk<T>(T(0), T(0));
+  ra = m + h;
+  rb = m - h;
+}
+
+// charpoly -> start roots -> classify -> Bairstow; the refined factors are then re-classified
+// (pair-aware) and re-paired once if the forward pair came out split across the two factors
+// (a noisy near-double start root can be misclassified when the loss is tiny).
 template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D) {
   cx<T> c3, c2, c1, c0;
   charpoly(D, c3, c2, c1, c0);
@@ -252,28 +288,23 @@ template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spec
     if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
   }
   cx<T> u = -sf, v = pf, b1, b0;
+  bool swap = false;
 #pragma unroll 1
-  for (int it = 0; it < 3; ++it) {
-    b1 = c3 - u;
-    b0 = c2 - u * b1 - v;
-    cx<T> r1 = c1 - u * b0 - v * b1;
-    cx<T> r0 = c0 - v * b0;
-    cx<T> umb = u - b1;
-    cx<T> j11 = v - b0 - u * umb;
-    cx<T> j12 = umb;
-    cx<T> j21 = -(v * umb);
-    cx<T> j22 = v - b0;
-    cx<T> det = j11 * j22 - j12 * j21;
-    if (norm2(det) > T(0)) {
-      cx<T> idet = recip(det);
-      u = u + (r0 * j12 - r1 * j22) * idet;
-      v = v + (r1 * j21 - r0 * j11) * idet;
-    }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    bairstow(c3, c2, c1, c0, u, v, b1, b0);
+    pair_roots(u, v, lam[0], lam[1]);
+    pair_roots(b1, b0, lam[2], lam[3]);
+    classify(lam, fwd);
+    const bool first = fwd[0] && fwd[1], second = fwd[2] && fwd[3];
+    swap = second && !first;
+    if (first || second || attempt == 1) break;
+    cx<T> ra = fwd[0] ? lam[0] : lam[1], rb = fwd[2] ? lam[2] : lam[3];
+    u = -(ra + rb);
+    v = ra * rb;
   }
-  b1 = c3 - u;
-  b0 = c2 - u * b1 - v;
   Spectrum<T> s;
-  s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
+  if (swap) { s.sf = -b1; s.pf = b0; s.sb = -u; s.pb = v; }
+  else { s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0; }
   return s;
 }
 

@@ -24,7 +24,10 @@ int fail(int code, const char* fmt, const char* detail = "") {
   return code;
 }
 
-constexpr int kThreads = 128;
+#ifndef HO_THREADS
+#define HO_THREADS 256
+#endif
+constexpr int kThreads = HO_THREADS;
 
 template <typename T> struct OutPtrs {
   ho::cx<T>* r_pp; ho::cx<T>* r_ps; ho::cx<T>* r_sp; ho::cx<T>* r_ss;

@@ -32,9 +32,19 @@ template <typename T> __device__ __forceinline__ cx<T> cmulc(cx<T> a, cx<T> b) {
   return mk<T>(a.re * b.re + a.im * b.im, a.re * b.im - a.im * b.re);
 }
 template <typename T> __device__ __forceinline__ cx<T> mul_i(cx<T> a) { return mk<T>(-a.im, a.re); }  // i*a
-template <typename T> __device__ __forceinline__ cx<T> recip(cx<T> a) {
-  T inv = T(1) / norm2(a);
-  return mk<T>(a.re * inv, -a.im * inv);
+__device__ __forceinline__ cx<double> recip(cx<double> a) {
+  double inv = 1.0 / norm2(a);
+  return mk<double>(a.re * inv, -a.im * inv);
+}
+// FP32: |a|^2 overflows already at |a| ~ 1.8e19 (the prism's 1/cos(theta) reaches 1.6e16 at the
+// grazing end points), so scale by the larger component first.
+__device__ __forceinline__ cx<float> recip(cx<float> a) {
+  float s = fmaxf(fabsf(a.re), fabsf(a.im));
+  if (!(s > 0.f)) return mk<float>(1.f / a.re, 0.f);
+  float is = 1.f / s;
+  float re = a.re * is, im = a.im * is;
+  float inv = is / (re * re + im * im);
+  return mk<float>(re * inv, -im * inv);
 }
 template <typename T> __device__ __forceinline__ cx<T> operator/(cx<T> a, cx<T> b) { return a * recip(b); }
 template <typename T> __device__ __forceinline__ cx<T> sel(bool c, cx<T> a, cx<T> b) { return c ? a : b; }

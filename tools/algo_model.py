@@ -80,7 +80,7 @@ def charpoly(D):
 
 
 # ----------------------------------------------------------------------------- quartic
-_OMEGA = np.exp(2j * np.pi / 3.0)
+_OMEGA = complex(np.exp(2j * np.pi / 3.0))  # python scalar: keeps complex64 inputs complex64
 
 
 def _ccbrt(z):
@@ -92,7 +92,7 @@ def _ccbrt(z):
 def _quad_roots(bq, cq):
     """Roots of y^2 + bq y + cq (cancellation-free)."""
     sq = np.sqrt(bq * bq - 4.0 * cq)
-    sgn = np.where((np.conj(bq) * sq).real >= 0.0, 1.0, -1.0)
+    sgn = np.where((np.conj(bq) * sq).real >= 0.0, 1.0, -1.0).astype(sq.real.dtype)
     t = -0.5 * (bq + sgn * sq)
     safe = np.abs(t) > 0.0
     y2 = np.where(safe, cq / np.where(safe, t, 1.0), 0.0)
@@ -101,7 +101,7 @@ def _quad_roots(bq, cq):
 
 def ferrari(c3, c2, c1, c0):
     """Closed-form roots (start values only; polished later)."""
-    c3 = c3.astype(np.complex128)
+    c3 = c3 + 0j  # dtype-preserving (complex64 stays complex64)
     q3 = 0.25 * c3
     p = c2 - 6.0 * q3 * q3
     q = c1 - 2.0 * q3 * c2 + 8.0 * q3 * q3 * q3
@@ -202,8 +202,22 @@ def bairstow(u, v, c3, c2, c1, c0, iters=3):
     return u, v, b1, b0
 
 
+def _pair_roots_for_classification(u, v, tau):
+    """Roots m +- h of lambda^2 + u lambda + v; a pair closer than sqrt(tau) (relative) is
+    treated as a double root at m so rounding noise in h cannot flip its classification."""
+    m = -0.5 * u
+    h = np.sqrt(m * m - v)
+    degenerate = np.abs(h) ** 2 <= tau * np.abs(m) ** 2
+    hh = np.where(degenerate, 0.0, h)
+    return m + hh, m - hh
+
+
 def split_spectrum(D, polish=0, bairstow_iters=3):
-    """-> (sf, pf, sb, pb, n_complex): sum/product of forward and backward root pairs."""
+    """-> (sf, pf, sb, pb, n_complex): sum/product of forward and backward root pairs.
+
+    start roots -> classify -> Bairstow; then the two refined quadratic factors are
+    re-classified (pair-aware) and, if the forward pair turns out to be split across the two
+    factors (possible when a noisy near-double start root was misclassified), re-paired once."""
     c3, c2, c1, c0 = charpoly(D)
     roots = ferrari(c3, c2, c1, c0)
     if polish:
@@ -211,8 +225,26 @@ def split_spectrum(D, polish=0, bairstow_iters=3):
     fwd, n_c = classify_forward(roots)
     sf = sum(np.where(fm, lam, 0.0) for fm, lam in zip(fwd, roots))
     pf = np.prod([np.where(fm, lam, 1.0) for fm, lam in zip(fwd, roots)], axis=0)
-    u, v, b1, b0 = bairstow(-sf, pf, c3, c2, c1, c0, bairstow_iters)
-    return -u, v, -b1, b0, n_c
+    tau = 1e-12 if np.asarray(c2).real.dtype == np.float64 else 1e-5
+    u, v = -sf, pf
+    for attempt in range(2):
+        u, v, b1, b0 = bairstow(u, v, c3, c2, c1, c0, bairstow_iters)
+        r0, r1 = _pair_roots_for_classification(u, v, tau)
+        r2, r3 = _pair_roots_for_classification(b1, b0, tau)
+        f4, _ = classify_forward([r0, r1, r2, r3])
+        first = f4[0] & f4[1]
+        second = f4[2] & f4[3]
+        mixed = ~(first | second)
+        if attempt == 1 or not np.any(mixed):
+            break
+        ra = np.where(f4[0], r0, r1)
+        rb = np.where(f4[2], r2, r3)
+        u = np.where(mixed, -(ra + rb), np.where(second, b1, u))
+        v = np.where(mixed, ra * rb, np.where(second, b0, v))
+    swap = second & ~first
+    uf, vf = np.where(swap, b1, u), np.where(swap, b0, v)
+    ub, vb = np.where(swap, u, b1), np.where(swap, v, b0)
+    return -uf, vf, -ub, vb, n_c
 
 
 def projector_coeffs(sf, pf, sb, pb):
