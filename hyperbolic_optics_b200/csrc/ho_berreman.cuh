@@ -126,9 +126,14 @@ template <typename T> __device__ __forceinline__ void charpoly(const Delta<T>& D
        + cg * cg + D.c * D.c * D.h * D.j - e2 * dj + D.d * D.f * D.g * D.g + dj * fh;
 }
 
-// roots of y^2 + bq y + cq without cancellation
+// Roots of y^2 + bq y + cq without cancellation.  A pair closer than ~sqrt(tau) relative to |bq|
+// is collapsed onto its mean: the split of a near-double root is rounding noise (~sqrt(eps)) and
+// could otherwise put its two copies on opposite sides of the forward/backward classification
+// when the loss is tiny (seen in FP32 on SiC at 1700 cm^-1).
 template <typename T> __device__ __forceinline__ void quad_roots(cx<T> bq, cx<T> cq, cx<T>& y0, cx<T>& y1) {
+  const T tau = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
   cx<T> sq = csqrt(bq * bq - T(4) * cq);
+  if (norm2(sq) <= tau * norm2(bq)) sq = mk<T>(T(0), T(0));
   bool plus = cmulc(bq, sq).re >= T(0);
   cx<T> t = T(-0.5) * (plus ? bq + sq : bq - sq);
   y0 = t;
@@ -171,29 +176,26 @@ template <typename T> __device__ __forceinline__ void ferrari(cx<T> c3, cx<T> c2
   lam[0] = y0 - q3; lam[1] = y1 - q3; lam[2] = y2 - q3; lam[3] = y3 - q3;
 }
 
-// Start values for the spectral split.  The closed form only has to be good enough to classify
-// the roots and to land inside Bairstow's basin, so it runs in FP32 (on the FP32 pipe, next to the
-// FP64 work of neighbouring warps); one guarded Newton step per root in working precision then
-// restores ~1e-12 accuracy before the forward/backward classification.
-__device__ __forceinline__ void start_roots(cx<float> c3, cx<float> c2, cx<float> c1, cx<float> c0, cx<float> lam[4]) {
-  // scale the roots to O(1) so the resolvent's sixth powers stay inside the FP32 range
-  float sc = fmaxf(fmaxf(cabs(c3), sqrtf(cabs(c2))), fmaxf(cbrtf(cabs(c1)), sqrtf(sqrtf(cabs(c0)))));
-  if (!(sc > 0.f) || !(sc < 3.0e38f)) sc = 1.f;
-  float is = 1.f / sc, is2 = is * is;
-  ferrari(is * c3, is2 * c2, (is2 * is) * c1, (is2 * is2) * c0, lam);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) lam[i] = sc * lam[i];
-}
+// Start values for the spectral split: always the FP64 closed form, also for the complex64
+// kernel.  An FP32 Ferrari was tried (it would run on the FP32 pipe next to the FP64 work) and
+// rejected: when both root pairs are nearly double (near-normal incidence on a c-cut uniaxial
+// film) the resolvent discriminant cancels catastrophically in FP32 and the start roots come out
+// ~8 % off with the wrong sign of Im -> wrong forward/backward classification (found by
+// tests/test_gpu_parity.py::test_backends_agree_at_scale).  -DHO_FERRARI_FP32 re-enables it.
 __device__ __forceinline__ void start_roots(cx<double> c3, cx<double> c2, cx<double> c1, cx<double> c0, cx<double> lam[4]) {
-#ifdef HO_FERRARI_FP64
+#ifndef HO_FERRARI_FP32
   ferrari(c3, c2, c1, c0, lam);
 #else
+  cx<float> f3 = mk<float>((float)c3.re, (float)c3.im), f2 = mk<float>((float)c2.re, (float)c2.im);
+  cx<float> f1 = mk<float>((float)c1.re, (float)c1.im), f0 = mk<float>((float)c0.re, (float)c0.im);
+  float sc = fmaxf(fmaxf(cabs(f3), sqrtf(cabs(f2))), fmaxf(cbrtf(cabs(f1)), sqrtf(sqrtf(cabs(f0)))));
+  if (!(sc > 0.f) || !(sc < 3.0e38f)) sc = 1.f;
+  float is = 1.f / sc, is2 = is * is;
   cx<float> l32[4];
-  start_roots(mk<float>((float)c3.re, (float)c3.im), mk<float>((float)c2.re, (float)c2.im),
-              mk<float>((float)c1.re, (float)c1.im), mk<float>((float)c0.re, (float)c0.im), l32);
+  ferrari(is * f3, is2 * f2, (is2 * is) * f1, (is2 * is2) * f0, l32);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    cx<double> x = mk<double>((double)l32[i].re, (double)l32[i].im);
+    cx<double> x = mk<double>((double)(sc * l32[i].re), (double)(sc * l32[i].im));
     cx<double> pv = fma(fma(fma(x + c3, x, c2), x, c1), x, c0);
     cx<double> dv = fma(fma(4.0 * x + 3.0 * c3, x, 2.0 * c2), x, c1);
     double dn = norm2(dv);
@@ -204,6 +206,12 @@ __device__ __forceinline__ void start_roots(cx<double> c3, cx<double> c2, cx<dou
     lam[i] = x;
   }
 #endif
+}
+__device__ __forceinline__ void start_roots(cx<float> c3, cx<float> c2, cx<float> c1, cx<float> c0, cx<float> lam[4]) {
+  cx<double> l64[4];
+  start_roots(mk<double>(c3.re, c3.im), mk<double>(c2.re, c2.im), mk<double>(c1.re, c1.im), mk<double>(c0.re, c0.im), l64);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) lam[i] = mk<float>((float)l64[i].re, (float)l64[i].im);
 }
 
 // Forward ("transmitted") pair selection, reference waves.py:273-289: all |Im| > 1e-9 -> two
@@ -261,20 +269,7 @@ template <typename T> __device__ __forceinline__ void bairstow(cx<T> c3, cx<T> c
   b0 = c2 - u * b1 - v;
 }
 
-// Roots m +- h of lambda^2 + u lambda + v for classification: a pair closer than sqrt(tau)
-// (relative) counts as a double root at m, so rounding noise in h cannot flip its side.
-template <typename T> __device__ __forceinline__ void pair_roots(cx<T> u, cx<T> v, cx<T>& ra, cx<T>& rb) {
-  const T tau = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
-  cx<T> m = T(-0.5) * u;
-  cx<T> h = csqrt(m * m - v);
-  if (norm2(h) <= tau * norm2(m)) h = mk<T>(T(0), T(0));
-  ra = m + h;
-  rb = m - h;
-}
-
-// charpoly -> start roots -> classify -> Bairstow; the refined factors are then re-classified
-// (pair-aware) and re-paired once if the forward pair came out split across the two factors
-// (a noisy near-double start root can be misclassified when the loss is tiny).
+// charpoly -> start roots -> forward pair -> Bairstow polish of that quadratic factor
 template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D) {
   cx<T> c3, c2, c1, c0;
   charpoly(D, c3, c2, c1, c0);
@@ -288,23 +283,9 @@ template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spec
     if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
   }
   cx<T> u = -sf, v = pf, b1, b0;
-  bool swap = false;
-#pragma unroll 1
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    bairstow(c3, c2, c1, c0, u, v, b1, b0);
-    pair_roots(u, v, lam[0], lam[1]);
-    pair_roots(b1, b0, lam[2], lam[3]);
-    classify(lam, fwd);
-    const bool first = fwd[0] && fwd[1], second = fwd[2] && fwd[3];
-    swap = second && !first;
-    if (first || second || attempt == 1) break;
-    cx<T> ra = fwd[0] ? lam[0] : lam[1], rb = fwd[2] ? lam[2] : lam[3];
-    u = -(ra + rb);
-    v = ra * rb;
-  }
+  bairstow(c3, c2, c1, c0, u, v, b1, b0);
   Spectrum<T> s;
-  if (swap) { s.sf = -b1; s.pf = b0; s.sb = -u; s.pb = v; }
-  else { s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0; }
+  s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   return s;
 }
 

@@ -90,8 +90,13 @@ def _ccbrt(z):
 
 
 def _quad_roots(bq, cq):
-    """Roots of y^2 + bq y + cq (cancellation-free)."""
+    """Roots of y^2 + bq y + cq (cancellation-free).  A pair closer than ~sqrt(tau) (relative to
+    |bq|) is collapsed onto its mean -bq/2: the split of a near-double root is rounding noise
+    (~sqrt(eps)), and letting it through can put the two copies on opposite sides of the
+    forward/backward classification when the loss is tiny."""
+    tau = 1e-12 if np.asarray(bq).real.dtype == np.float64 else 1e-5
     sq = np.sqrt(bq * bq - 4.0 * cq)
+    sq = np.where(np.abs(sq) ** 2 <= tau * np.abs(bq) ** 2, 0.0, sq)
     sgn = np.where((np.conj(bq) * sq).real >= 0.0, 1.0, -1.0).astype(sq.real.dtype)
     t = -0.5 * (bq + sgn * sq)
     safe = np.abs(t) > 0.0
@@ -202,22 +207,8 @@ def bairstow(u, v, c3, c2, c1, c0, iters=3):
     return u, v, b1, b0
 
 
-def _pair_roots_for_classification(u, v, tau):
-    """Roots m +- h of lambda^2 + u lambda + v; a pair closer than sqrt(tau) (relative) is
-    treated as a double root at m so rounding noise in h cannot flip its classification."""
-    m = -0.5 * u
-    h = np.sqrt(m * m - v)
-    degenerate = np.abs(h) ** 2 <= tau * np.abs(m) ** 2
-    hh = np.where(degenerate, 0.0, h)
-    return m + hh, m - hh
-
-
 def split_spectrum(D, polish=0, bairstow_iters=3):
-    """-> (sf, pf, sb, pb, n_complex): sum/product of forward and backward root pairs.
-
-    start roots -> classify -> Bairstow; then the two refined quadratic factors are
-    re-classified (pair-aware) and, if the forward pair turns out to be split across the two
-    factors (possible when a noisy near-double start root was misclassified), re-paired once."""
+    """-> (sf, pf, sb, pb, n_complex): sum/product of forward and backward root pairs."""
     c3, c2, c1, c0 = charpoly(D)
     roots = ferrari(c3, c2, c1, c0)
     if polish:
@@ -225,26 +216,8 @@ def split_spectrum(D, polish=0, bairstow_iters=3):
     fwd, n_c = classify_forward(roots)
     sf = sum(np.where(fm, lam, 0.0) for fm, lam in zip(fwd, roots))
     pf = np.prod([np.where(fm, lam, 1.0) for fm, lam in zip(fwd, roots)], axis=0)
-    tau = 1e-12 if np.asarray(c2).real.dtype == np.float64 else 1e-5
-    u, v = -sf, pf
-    for attempt in range(2):
-        u, v, b1, b0 = bairstow(u, v, c3, c2, c1, c0, bairstow_iters)
-        r0, r1 = _pair_roots_for_classification(u, v, tau)
-        r2, r3 = _pair_roots_for_classification(b1, b0, tau)
-        f4, _ = classify_forward([r0, r1, r2, r3])
-        first = f4[0] & f4[1]
-        second = f4[2] & f4[3]
-        mixed = ~(first | second)
-        if attempt == 1 or not np.any(mixed):
-            break
-        ra = np.where(f4[0], r0, r1)
-        rb = np.where(f4[2], r2, r3)
-        u = np.where(mixed, -(ra + rb), np.where(second, b1, u))
-        v = np.where(mixed, ra * rb, np.where(second, b0, v))
-    swap = second & ~first
-    uf, vf = np.where(swap, b1, u), np.where(swap, b0, v)
-    ub, vb = np.where(swap, u, b1), np.where(swap, v, b0)
-    return -uf, vf, -ub, vb, n_c
+    u, v, b1, b0 = bairstow(-sf, pf, c3, c2, c1, c0, bairstow_iters)
+    return -u, v, -b1, b0, n_c
 
 
 def projector_coeffs(sf, pf, sb, pb):
