@@ -5,10 +5,11 @@ Drop-in for the hot path of hyperbolic-optics 0.3.0 (``Structure.execute`` ->
 hand-written sm_100a CUDA kernels through the C ABI in ``include/ho_b200.h``.
 """
 
+from .fields import FieldProfile
 from .materials import create_material, list_materials
 from .mueller import Mueller
 from .scenario import ScenarioSetup
 from .structure import Structure
 
 __version__ = "0.1.0"
-__all__ = ["Structure", "ScenarioSetup", "Mueller", "create_material", "list_materials", "__version__"]
+__all__ = ["Structure", "ScenarioSetup", "Mueller", "FieldProfile", "create_material", "list_materials", "__version__"]

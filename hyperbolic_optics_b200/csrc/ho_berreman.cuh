@@ -378,7 +378,9 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 
 // Stable propagation of the plane span(Y) through a film: only decaying exponentials.
 // Renormalises so that rows (Ex, Ey) of the forward part are the identity.
-template <typename T, bool NM> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
+// w[0..3] = (w00, w01, w10, w11): the 2x2 map W with Y_new = exp(cD) Y_old W, i.e. coordinates at
+// the top of the film -> coordinates at its bottom (used by the power bookkeeping only).
+template <typename T, bool NM> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   Vec4<T> dy;
@@ -401,6 +403,8 @@ template <typename T, bool NM> __device__ __forceinline__ void film_stable(const
   Vec4<T> e1 = lin_apply(phi, dd, lam, xb1, matvec(D, xb1));
   y0 = axpy(g0.v1, e1, axpy(g0.v0, e0, xf0));
   y1 = axpy(g1.v1, e1, axpy(g1.v0, e0, xf1));
+  w[0] = fma(n01, g0.v1, n00 * g0.v0); w[1] = fma(n01, g1.v1, n00 * g1.v0);
+  w[2] = fma(n11, g0.v1, n10 * g0.v0); w[3] = fma(n11, g1.v1, n10 * g1.v0);
 }
 
 // Forward invariant subspace of a semi-infinite crystal: P_f [e0 e1].  With unit seeds the first
@@ -425,7 +429,7 @@ template <typename T> __device__ __forceinline__ Vec4<T> iso_matvec(cx<T> d, cx<
   Vec4<T> r; r.v0 = d * v.v3; r.v1 = f * v.v2; r.v2 = h * v.v1; r.v3 = j * v.v0; return r;
 }
 
-template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, cx<T> mu, cx<T> c, bool stable, Vec4<T>& y0, Vec4<T>& y1) {
+template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, cx<T> mu, cx<T> c, bool stable, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   T k2 = k * k;
   cx<T> d = mu - k2 * recip(eps), f = -mu, h = k2 * recip(mu) - eps, j = eps;
   cx<T> kz2 = eps * mu - k2;
@@ -461,6 +465,8 @@ template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, c
   inv2(zf0.v0, zf1.v0, zf0.v1, zf1.v1, n00, n01, n10, n11);
   y0 = axpy(ph2, axpy(n10, zb1, scale(n00, zb0)), axpy(n10, zf1, scale(n00, zf0)));
   y1 = axpy(ph2, axpy(n11, zb1, scale(n01, zb0)), axpy(n11, zf1, scale(n01, zf0)));
+  cx<T> ph = cexp(-(c * kz));  // exp(i tau kz): |.| <= 1
+  w[0] = n00 * ph; w[1] = n01 * ph; w[2] = n10 * ph; w[3] = n11 * ph;
 }
 
 // columns 0 and 2 of the isotropic exit matrix (reference layers.py:190-238)
@@ -482,6 +488,32 @@ template <typename T> __device__ __forceinline__ void reflect_from_plane(const V
   r_ps = (g00 * g12 - g10 * g02) * ib;
   r_sp = (g30 * g22 - g32 * g20) * ib;
   r_ss = (g10 * g22 - g12 * g20) * ib;
+}
+
+// ---- power bookkeeping (reference fields.py:45-51, 120-282) ----
+// Hermitian 2x2 form of S_z = 1/2 Re(Ex Hy* - Ey Hx*) on the plane Y c:
+//   S_z = h[0] |c0|^2 + h[1] |c1|^2 + Re(c0 conj(c1) (h[2] + i h[3]))
+template <typename T> __device__ __forceinline__ void flux_form(const Vec4<T>& y0, const Vec4<T>& y1, T h[4]) {
+  cx<T> q00 = cmulc(y0.v3, y0.v0) - cmulc(y0.v2, y0.v1);
+  cx<T> q11 = cmulc(y1.v3, y1.v0) - cmulc(y1.v2, y1.v1);
+  cx<T> q01 = cmulc(y1.v3, y0.v0) - cmulc(y1.v2, y0.v1);
+  cx<T> q10 = cmulc(y0.v3, y1.v0) - cmulc(y0.v2, y1.v1);
+  h[0] = T(0.5) * q00.re; h[1] = T(0.5) * q11.re;
+  h[2] = T(0.5) * (q01.re + q10.re); h[3] = T(0.5) * (q01.im - q10.im);
+}
+template <typename T> __device__ __forceinline__ T flux_eval(const T h[4], cx<T> c0, cx<T> c1) {
+  cx<T> z = cmulc(c1, c0);
+  return h[0] * norm2(c0) + h[1] * norm2(c1) + (z.re * h[2] - z.im * h[3]);
+}
+// Coordinates c of the field on the top plane for unit incident s / p amplitude: solves
+// [[G00, G02], [G20, G22]] c = (a_s, a_p), G = M_prism Y with the prism's 1/2 kept (fields.py:120-145)
+template <typename T> __device__ __forceinline__ void incident_coords(const Vec4<T>& y0, const Vec4<T>& y1, T inv_c, T inv_nc, T inv_n,
+                                                                     cx<T>& cp0, cx<T>& cp1, cx<T>& cs0, cx<T>& cs1) {
+  cx<T> g00 = T(0.5) * (y0.v1 - inv_nc * y0.v2), g20 = T(0.5) * (inv_c * y0.v0 + inv_n * y0.v3);
+  cx<T> g02 = T(0.5) * (y1.v1 - inv_nc * y1.v2), g22 = T(0.5) * (inv_c * y1.v0 + inv_n * y1.v3);
+  cx<T> idet = recip(g00 * g22 - g02 * g20);
+  cp0 = -(g02 * idet); cp1 = g00 * idet;   // (a_s, a_p) = (0, 1)
+  cs0 = g22 * idet;    cs1 = -(g20 * idet);  // (a_s, a_p) = (1, 0)
 }
 
 // Mueller matrix M = Re(A F A^-1), F = J (x) J* in the reference's layout (mueller.py:266-307)

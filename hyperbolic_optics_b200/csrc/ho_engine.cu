@@ -33,6 +33,7 @@ template <typename T> struct OutPtrs {
   ho::cx<T>* r_pp; ho::cx<T>* r_ps; ho::cx<T>* r_sp; ho::cx<T>* r_ss;
   T* mueller; T* stokes;
   T s_in[4];
+  T* power; int64_t power_stride;
 };
 
 template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p) {
@@ -68,7 +69,8 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 
 // NM: every crystal layer of the stack has mu proportional to the identity (all built-in
 // materials) -> sparser Berreman matrix; the general kernel handles full mu tensors.
-template <typename T, bool STABLE, bool NM>
+// POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
+template <typename T, bool STABLE, bool NM, bool POWER>
 __global__ void __launch_bounds__(kThreads, HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end) {
   using namespace ho;
@@ -84,9 +86,14 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     const T k0 = T(__ldg(P.k0 + f));
 
     Vec4<T> y0, y1;
+    // POWER only (dead otherwise): flux form at the top of every layer and, for the stable
+    // recursion, the coordinate map through every film
+    T hf[POWER ? HO_MAX_LAYERS : 1][4];
+    cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
       const ho_layer_t& L = P.layers[l];
+      cx<T> w[4];
       if (L.kind == HO_ISO_EXIT) {
         exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
       } else if (L.kind == HO_ANISO_EXIT) {
@@ -97,13 +104,17 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
         const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
         const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
         if (L.kind == HO_ISO_FILM) {
-          iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1);
+          iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
         } else {
           Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
           Spectrum<T> s = split_spectrum(D);
-          if (STABLE) film_stable(D, s, c, y0, y1);
+          if (STABLE) film_stable(D, s, c, y0, y1, w);
           else film_transfer(D, s, c, y0, y1);
         }
+      }
+      if constexpr (POWER) {
+        flux_form(y0, y1, hf[l]);
+        if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
       }
     }
 
@@ -111,6 +122,33 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     reflect_from_plane(y0, y1, T(__ldg(P.prism_inv_cos + a)), T(__ldg(P.prism_inv_ncos + a)), T(P.prism_inv_n),
                        r_pp, r_ps, r_sp, r_ss);
     const int64_t o = n - n_begin;
+    if constexpr (POWER) {
+      // planes [pol][R, T, A_0 .. A_{L-2}], pol 0 = p, 1 = s; fluxes walk top -> bottom
+      const T inv_c = T(__ldg(P.prism_inv_cos + a)), inv_nc = T(__ldg(P.prism_inv_ncos + a));
+      cx<T> c0[2], c1[2];
+      incident_coords(y0, y1, inv_c, inv_nc, T(P.prism_inv_n), c0[0], c1[0], c0[1], c1[1]);
+      const T inv_sinc = T(2) * inv_nc;  // 1 / S_z^inc, S_z^inc = n cos(theta) / 2
+      const int n_planes = P.n_layers + 1;
+#pragma unroll
+      for (int pol = 0; pol < 2; ++pol) {
+        T* dst = out.power + (int64_t)pol * n_planes * out.power_stride + o;
+        cx<T> a0 = c0[pol], a1 = c1[pol];
+        T prev = flux_eval(hf[0], a0, a1);
+        dst[0] = T(1) - prev * inv_sinc;
+#pragma unroll 1
+        for (int l = 1; l < P.n_layers; ++l) {
+          if constexpr (STABLE) {
+            cx<T> b0 = fma(wm[l - 1][1], a1, wm[l - 1][0] * a0);
+            a1 = fma(wm[l - 1][3], a1, wm[l - 1][2] * a0);
+            a0 = b0;
+          }
+          T cur = flux_eval(hf[l], a0, a1);
+          dst[(int64_t)(1 + l) * out.power_stride] = (prev - cur) * inv_sinc;
+          prev = cur;
+        }
+        dst[out.power_stride] = prev * inv_sinc;
+      }
+    }
     if (out.r_pp) out.r_pp[o] = r_pp;
     if (out.r_ps) out.r_ps[o] = r_ps;
     if (out.r_sp) out.r_sp[o] = r_sp;
@@ -200,12 +238,20 @@ int grid_for(int64_t n, const void* kernel) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+template <typename T, bool STABLE, bool NM, bool POWER>
+int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
+  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER>;
+  int grid = grid_for(n_end - n_begin, kern);
+  reflect_kernel<T, STABLE, NM, POWER><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end);
+  return 0;
+}
+
 template <typename T, bool STABLE, bool NM>
 int launch_nm(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
-  const void* kern = (const void*)reflect_kernel<T, STABLE, NM>;
-  int grid = grid_for(n_end - n_begin, kern);
-  reflect_kernel<T, STABLE, NM><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end);
-  return 0;
+  if constexpr (sizeof(T) == 8) {
+    if (out.power) return launch_k<T, STABLE, NM, true>(p, out, n_begin, n_end, stream);
+  }
+  return launch_k<T, STABLE, NM, false>(p, out, n_begin, n_end, stream);
 }
 
 template <typename T, bool STABLE>
@@ -238,6 +284,9 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
   o.mueller = out->mueller;
   o.stokes = out->stokes;
   for (int i = 0; i < 4; ++i) o.s_in[i] = out->incident_stokes[i];
+  o.power = out->power;
+  o.power_stride = out->power_stride;
+  if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<double, true>(problem, o, n_begin, n_end, s)
                                                    : launch<double, false>(problem, o, n_begin, n_end, s);
@@ -255,6 +304,8 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.mueller = out->mueller;
   o.stokes = nullptr;
   for (int i = 0; i < 4; ++i) o.s_in[i] = 0.f;
+  o.power = nullptr;
+  o.power_stride = 0;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, n_begin, n_end, s)
                                                    : launch<float, false>(problem, o, n_begin, n_end, s);

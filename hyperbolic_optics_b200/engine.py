@@ -99,7 +99,7 @@ class DeviceProblem:
 class DeviceOutputs:
     """Caller-owned output buffers for a contiguous range of batch points."""
 
-    def __init__(self, n, device, mueller=True, stokes=None, dtype=torch.complex128):
+    def __init__(self, n, device, mueller=True, stokes=None, dtype=torch.complex128, power_planes=0):
         self.n = n
         self.dtype = dtype
         real = torch.float64 if dtype == torch.complex128 else torch.float32
@@ -107,11 +107,13 @@ class DeviceOutputs:
         self.mueller = torch.empty((n, 4, 4), dtype=real, device=device) if mueller else None
         self.stokes = torch.empty((n, 4), dtype=real, device=device) if stokes is not None else None
         self.incident_stokes = stokes
+        # power bookkeeping planes [2 * (n_layers + 1)][n]: per polarisation R, T, A_0 .. A_{L-2}
+        self.power = torch.empty((power_planes, n), dtype=real, device=device) if power_planes else None
 
     @property
     def nbytes(self):
         total = self.r.numel() * self.r.element_size()
-        for t in (self.mueller, self.stokes):
+        for t in (self.mueller, self.stokes, self.power):
             if t is not None:
                 total += t.numel() * t.element_size()
         return total
@@ -131,6 +133,10 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
         o.stokes = out.stokes.data_ptr() if out.stokes is not None else None
         if out.incident_stokes is not None:
             o.incident_stokes = (C.c_double * 4)(*[float(x) for x in out.incident_stokes])
+        if out.power is not None:
+            if out.power.shape[0] != 2 * (len(problem.plan.layers) + 1):
+                raise ValueError("power buffer must have 2 * (n_layers + 1) planes")
+            o.power, o.power_stride = out.power.data_ptr(), out.power.shape[1]
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:
         o = nat.OutputsF32()

@@ -13,7 +13,9 @@ same errors (``ValueError`` for an unknown backend / layer type / second swept t
 error: the transfer backend returns inf/NaN where the reference's 4x4 product overflows.
 
 Additions (all optional): ``mueller`` (the sample Mueller matrix, fused into the same
-kernel), ``stokes`` for a given incident Stokes vector, ``device=`` / ``keep_on_device=``.
+kernel), ``stokes`` for a given incident Stokes vector, ``power=True`` (R, T and layer-resolved
+absorption for p and s incidence from the same launch, both backends; consumed by
+``hyperbolic_optics_b200.FieldProfile``), ``device=`` / ``keep_on_device=``.
 
 What is *not* materialised: per-layer 4x4 matrices, eigenvector profiles and
 ``transfer_matrix`` -- the kernel keeps a 4x2 plane in registers instead,
@@ -65,6 +67,8 @@ class Structure:
         self.device = device
         self.chunk_points = int(chunk_points)
         self.with_mueller = True
+        self.with_power = False
+        self.power = None
         self.incident_stokes = None
         self.keep_on_device = False
         # True: results are private NumPy copies (drop-in semantics).  False: zero-copy views of
@@ -110,10 +114,11 @@ class Structure:
 
     # -- one-call protocol ---------------------------------------------------------------
     def execute(self, payload, backend="transfer", mueller=True, incident_stokes=None,
-                keep_on_device=False, own_results=None):
+                keep_on_device=False, own_results=None, power=False):
         if backend not in ("transfer", "scattering"):
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
         self.with_mueller = bool(mueller)
+        self.with_power = bool(power)
         self.incident_stokes = incident_stokes
         self.keep_on_device = bool(keep_on_device)
         if own_results is not None:
@@ -130,11 +135,12 @@ class Structure:
         n = plan.n_points
         shape = plan.fabt_shape
         want_stokes = self.incident_stokes is not None
+        planes = 2 * (len(plan.layers) + 1) if self.with_power else 0
         if self.keep_on_device:
-            out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes)
+            out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes)
             engine.reflect(prob, out)
             r = out.r.reshape((4,) + shape)
-            self._assign(r, out.mueller, out.stokes, shape, to_numpy=False)
+            self._assign(r, out.mueller, out.stokes, out.power, shape, to_numpy=False)
             self.d2h_bytes = 0
             return
         # host results: kernel -> device chunk (double buffered) -> pinned host, D2H on a copy stream
@@ -142,7 +148,8 @@ class Structure:
         host_r = _pinned("r", (4, n), torch.complex128)
         host_m = _pinned("m", (n, 4, 4), torch.float64) if self.with_mueller else None
         host_s = _pinned("s", (n, 4), torch.float64) if want_stokes else None
-        bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes)
+        host_p = _pinned("p", (planes, n), torch.float64) if planes else None
+        bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes)
                 for _ in range(2 if n > chunk else 1)]
         compute = torch.cuda.current_stream(prob.device)
         copy = torch.cuda.Stream(prob.device)
@@ -164,14 +171,16 @@ class Structure:
                     host_m[start:stop].copy_(buf.mueller[:m], non_blocking=True)
                 if host_s is not None:
                     host_s[start:stop].copy_(buf.stokes[:m], non_blocking=True)
+                for i in range(planes):
+                    host_p[i, start:stop].copy_(buf.power[i, :m], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             done[ci % len(bufs)] = ev
         copy.synchronize()
-        self.d2h_bytes = n * (64 + (128 if host_m is not None else 0) + (32 if host_s is not None else 0))
-        self._assign(host_r.reshape((4,) + shape), host_m, host_s, shape, to_numpy=True)
+        self.d2h_bytes = n * (64 + (128 if host_m is not None else 0) + (32 if host_s is not None else 0) + 8 * planes)
+        self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, shape, to_numpy=True)
 
-    def _assign(self, r, mueller, stokes, shape, to_numpy):
+    def _assign(self, r, mueller, stokes, power, shape, to_numpy):
         if to_numpy:
             conv = (lambda t: np.array(t.numpy())) if self.own_results else (lambda t: t.numpy())
         else:
@@ -180,6 +189,14 @@ class Structure:
         self.r_pp, self.r_ps, self.r_sp, self.r_ss = (pres(conv(r[i])) for i in range(4))
         self.mueller = pres(conv(mueller.reshape(shape + (4, 4)))) if mueller is not None else None
         self.stokes = pres(conv(stokes.reshape(shape + (4,)))) if stokes is not None else None
+        self.power = None
+        if power is not None:
+            # planes per polarisation: R, T, A_0 .. A_{L-2}  (include/ho_b200.h, ho_outputs_t.power)
+            per = power.shape[0] // 2
+            self.power = {}
+            for pi, pol in enumerate("ps"):
+                blk = [pres(conv(power[pi * per + k].reshape(shape))) for k in range(per)]
+                self.power[pol] = {"R": blk[0], "T": blk[1], "A": blk[2:]}
 
 
 def _present_torch(t):

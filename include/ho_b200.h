@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 1
+#define HO_ABI_VERSION 2
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -97,6 +97,14 @@ typedef struct {
   /* [n][4] Stokes vector M * incident_stokes (mueller.py:479-500); needs mueller math only */
   double* stokes;
   double incident_stokes[4];
+  /* Power bookkeeping, replaces FieldProfile.reflectance / transmittance / layer_absorption
+     (fields.py:120-282) for pure p and s incidence, valid for BOTH backends (the reference's
+     FieldProfile needs the transfer matrix, fields.py:87-88).  2*(n_layers+1) planes of
+     power_stride doubles each, plane index pol*(n_layers+1) + k with pol 0 = p, 1 = s and
+     k = 0: R = 1 - S_z(G_1)/S_inc, k = 1: T = S_z(G_exit)/S_inc, k = 2+i: absorptance of the
+     i-th finite layer below the prism (i = 0 .. n_layers-2).  NULL to skip. */
+  double* power;
+  int64_t power_stride; /* >= n_end - n_begin */
 } ho_outputs_t;
 
 /* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /

@@ -349,7 +349,7 @@ def _inv2(m00, m01, m10, m11):
     return m11 * idet, -m01 * idet, -m10 * idet, m00 * idet
 
 
-def film_stable(D, Y, spec, cfac, rows=(0, 1)):
+def film_stable(D, Y, spec, cfac, rows=(0, 1), return_w=False):
     """Stable (scattering-equivalent) propagation of the plane spanned by Y through a film.
 
     Returns the renormalised plane X_f + G_b Z_b N (L G_f^-1 X_f) using only decaying
@@ -383,6 +383,11 @@ def film_stable(D, Y, spec, cfac, rows=(0, 1)):
         gb.append(tuple((Ab - Bb * mb) * x[i] + Bb * dx[i] for i in range(4)))
     out = [tuple(xf[cidx][i] + gb[0][i] * gcols[cidx][0] + gb[1][i] * gcols[cidx][1] for i in range(4))
            for cidx in range(2)]
+    if return_w:
+        # W = N G: coordinates at the top of the film -> coordinates at its bottom (Y_new = M Y_old W)
+        w = ((n00 * gcols[0][0] + n01 * gcols[0][1], n00 * gcols[1][0] + n01 * gcols[1][1]),
+             (n10 * gcols[0][0] + n11 * gcols[0][1], n10 * gcols[1][0] + n11 * gcols[1][1]))
+        return out, w
     return out
 
 
@@ -425,7 +430,7 @@ def iso_forward_kz(k, eps, mu):
     return np.where(fwd, kz, -kz)
 
 
-def iso_film_stable(k, eps, mu, Y, cfac, rows=(0, 1)):
+def iso_film_stable(k, eps, mu, Y, cfac, rows=(0, 1), return_w=False):
     D = iso_delta(k, eps, mu)
     kz = iso_forward_kz(k, eps, mu)
     ikz = 1.0 / kz
@@ -442,6 +447,9 @@ def iso_film_stable(k, eps, mu, Y, cfac, rows=(0, 1)):
     for (ca, cb) in ((n00, n10), (n01, n11)):
         out.append(tuple(zf[0][i] * ca + zf[1][i] * cb + phase2 * (zb[0][i] * ca + zb[1][i] * cb)
                          for i in range(4)))
+    if return_w:
+        ph = np.exp(-cfac * kz)  # exp(i tau kz), decaying
+        return out, ((n00 * ph, n01 * ph), (n10 * ph, n11 * ph))
     return out
 
 
@@ -487,3 +495,28 @@ def mueller(pp, ps, sp, ss):
         M[..., r, 2] = 0.5 * (c1 + c2).real
         M[..., r, 3] = (0.5j * (c2 - c1)).real
     return M
+
+
+# ----------------------------------------------------------------------------- power bookkeeping
+def flux_form(Y):
+    """Hermitian 2x2 form of S_z = 1/2 Re(Ex Hy* - Ey Hx*) on the plane Y c (reference
+    fields.py:45-51): S_z = h00 |c0|^2 + h11 |c1|^2 + Re(c0 conj(c1) h01)."""
+    def q(u, v):
+        return u[0] * np.conj(v[3]) - u[1] * np.conj(v[2])
+    y0, y1 = Y
+    return 0.5 * q(y0, y0).real, 0.5 * q(y1, y1).real, 0.5 * (q(y0, y1) + np.conj(q(y1, y0)))
+
+
+def flux_eval(h, c):
+    h00, h11, h01 = h
+    return h00 * np.abs(c[0]) ** 2 + h11 * np.abs(c[1]) ** 2 + (c[0] * np.conj(c[1]) * h01).real
+
+
+def incident_coords(Y, inv_c, inv_nc, inv_n, a_s, a_p):
+    """Solve [[G00, G02], [G20, G22]] c = (a_s, a_p) with G = M_prism Y (1/2 included)."""
+    g = []
+    for y in Y:
+        g.append((0.5 * (y[1] - y[2] * inv_nc), 0.5 * (y[0] * inv_c + y[3] * inv_n)))
+    (g00, g20), (g02, g22) = g
+    idet = 1.0 / (g00 * g22 - g02 * g20)
+    return (g22 * a_s - g02 * a_p) * idet, (g00 * a_p - g20 * a_s) * idet

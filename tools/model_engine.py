@@ -39,11 +39,13 @@ def run(plan, backend="transfer", stats=None, **kw):
     k0 = plan.k0[f]
     stable = backend == "scattering"
     Y = None
+    forms, maps = [], []  # per layer (bottom -> top): flux form at its top interface, W (stable)
     with np.errstate(all="ignore"):
         for lp in reversed(plan.layers):
             if lp.kind == P.KIND_ISO_EXIT:
                 cf = lp.exit_cos[a]
                 Y = am.exit_iso_plane(cf, lp.exit_n + 0j)
+                forms.append(am.flux_form(Y)); maps.append(None)
                 continue
             if lp.kind == P.KIND_ANISO_EXIT:
                 D = layer_delta(plan, lp, f, a, b)
@@ -51,6 +53,7 @@ def run(plan, backend="transfer", stats=None, **kw):
                 if stats is not None:
                     stats.setdefault("n_complex", []).append(spec[4])
                 Y = am.substrate_plane(D, spec[:4])
+                forms.append(am.flux_form(Y)); maps.append(None)
                 continue
             d = _pick(lp.thickness, t)
             cfac = -1j * k0 * d
@@ -58,8 +61,9 @@ def run(plan, backend="transfer", stats=None, **kw):
                 eps = lp.iso_eps + 0 * k
                 mu = lp.iso_mu + 0 * k
                 if stable:
-                    Y = am.iso_film_stable(k, eps, mu, Y, cfac)
+                    Y, w = am.iso_film_stable(k, eps, mu, Y, cfac, return_w=True)
                 else:
+                    w = None
                     Y = am.iso_film_transfer(k, eps, mu, Y, cfac)
             else:
                 D = layer_delta(plan, lp, f, a, b)
@@ -67,13 +71,29 @@ def run(plan, backend="transfer", stats=None, **kw):
                 if stats is not None:
                     stats.setdefault("n_complex", []).append(spec[4])
                 if stable:
-                    Y = am.film_stable(D, Y, spec[:4], cfac)
+                    Y, w = am.film_stable(D, Y, spec[:4], cfac, return_w=True)
                 else:
+                    w = None
                     Y = am.film_transfer(D, Y, spec[:4], cfac)
+            forms.append(am.flux_form(Y)); maps.append(w)
         r_pp, r_ps, r_sp, r_ss = am.reflect_from_plane(
             Y, plan.prism_inv_cos[a], plan.prism_inv_ncos[a], plan.prism_inv_n)
         mu4 = am.mueller(r_pp, r_ps, r_sp, r_ss)
-    return {"r_pp": r_pp, "r_ps": r_ps, "r_sp": r_sp, "r_ss": r_ss, "mueller": mu4}
+        out = {"r_pp": r_pp, "r_ps": r_ps, "r_sp": r_sp, "r_ss": r_ss, "mueller": mu4}
+        # power bookkeeping (reference fields.py:120-282): fluxes at every interface, top -> bottom
+        inv_c, inv_nc = plan.prism_inv_cos[a], plan.prism_inv_ncos[a]
+        s_inc = 0.5 / inv_nc
+        for pol, (a_s, a_p) in (("p", (0.0, 1.0)), ("s", (1.0, 0.0))):
+            c = am.incident_coords(Y, inv_c, inv_nc, plan.prism_inv_n, a_s, a_p)
+            flux = []
+            for h, w in zip(reversed(forms), reversed(maps)):
+                flux.append(am.flux_eval(h, c))
+                if w is not None:
+                    c = (w[0][0] * c[0] + w[0][1] * c[1], w[1][0] * c[0] + w[1][1] * c[1])
+            out[f"R_{pol}"] = 1.0 - flux[0] / s_inc
+            out[f"T_{pol}"] = flux[-1] / s_inc
+            out[f"A_{pol}"] = [(flux[i] - flux[i + 1]) / s_inc for i in range(len(flux) - 1)]
+    return out
 
 
 def jones_error(got, ref):
