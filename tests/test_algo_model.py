@@ -32,3 +32,23 @@ def test_model_matches_reference(name):
             scale = np.maximum(np.abs(fx["mueller"]).max(axis=(-1, -2)), 1e-300)
             merr = np.abs(mu - fx["mueller"]).max(axis=(-1, -2)) / scale
             assert np.nanmax(merr[mask]) <= parity.TOL_C128
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if "R_p" in parity.load_fixture(n)])
+def test_model_power_bookkeeping(name):
+    """Flux-form power bookkeeping of the device algorithm (both recursions) vs the reference's
+    transfer + FieldProfile fixtures (fields.py:120-282)."""
+    fx = parity.load_fixture(name)
+    sc, payload = parity.scenario_for(name, ScenarioSetup)
+    plan = build_plan(sc, payload["Layers"])
+    mask = parity.transfer_mask(fx)
+    for backend in ("transfer", "scattering"):
+        out = model_engine.run(plan, backend)
+        tol = 1e-5 if (name.startswith("c5") and backend == "transfer") else 1e-10
+        for pol in "ps":
+            vals = {f"R_{pol}": out[f"R_{pol}"], f"T_{pol}": out[f"T_{pol}"]}
+            vals.update({f"A_{pol}{i + 1}": a for i, a in enumerate(out[f"A_{pol}"])})
+            for key, val in vals.items():
+                err = np.abs(parity.subsample(present(val), fx["strides"]) - fx[key])
+                err = err[mask] if np.ndim(err) else err
+                assert np.nanmax(err) <= tol, f"{name}/{backend}/{key}: {np.nanmax(err):.2e}"
