@@ -158,11 +158,13 @@ template <typename T> __device__ __forceinline__ void ferrari(cx<T> c3, cx<T> c2
   cx<T> third_p = T(1.0 / 3.0) * p;
   cx<T> m = mk<T>(T(0), T(0));
   T best = T(-1);
+  // P / (3 u w^k) = (P / 3u) conj(w^k): one reciprocal serves the three cube roots
+  const bool u_ok = norm2(u) > T(0);
+  cx<T> pu = u_ok ? T(1.0 / 3.0) * (P * recip(u)) : mk<T>(T(0), T(0));
 #pragma unroll
   for (int kk = 0; kk < 3; ++kk) {
     cx<T> uk = (kk == 0) ? u : (kk == 1 ? u * w1 : u * w2);
-    cx<T> tk = uk;
-    if (norm2(uk) > T(0)) tk = uk - T(1.0 / 3.0) * (P / uk);
+    cx<T> tk = uk - ((kk == 0) ? pu : (kk == 1 ? pu * w2 : pu * w1));
     cx<T> mk_ = tk - third_p;
     T ak = norm2(mk_);
     if (ak > best) { best = ak; m = mk_; }
@@ -246,44 +248,88 @@ template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4
 }
 
 // Bairstow: Newton on (u, v) so that lambda^2 + u lambda + v divides the quartic; the
-// complementary factor lambda^2 + b1 lambda + b0 follows by deflation.
-template <typename T> __device__ __forceinline__ void bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0) {
+// complementary factor lambda^2 + b1 lambda + b0 follows by deflation.  Per-point early exits:
+// the Newton step is skipped once the residual of the division is at rounding level, and the
+// loop ends once a step is negligible (accurate start values need exactly one step).
+template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0) {
+  const T res_tol2 = sizeof(T) == 8 ? T(1e-28) : T(1e-12);
+  const T step_tol2 = sizeof(T) == 8 ? T(1e-22) : T(1e-7);
+  const int max_steps = 3;
+  bool converged = false;
 #pragma unroll 1
-  for (int it = 0; it < 3; ++it) {
+  for (int it = 0;; ++it) {
     b1 = c3 - u;
-    b0 = c2 - u * b1 - v;
-    cx<T> r1 = c1 - u * b0 - v * b1;
-    cx<T> r0 = c0 - v * b0;
+    b0 = c2 - v - u * b1;
+    cx<T> t1 = u * b0, t2 = v * b1, t3 = v * b0;
+    cx<T> r1 = c1 - t1 - t2;
+    cx<T> r0 = c0 - t3;
+    if (it > 0 && norm2(r1) <= res_tol2 * (norm2(t1) + norm2(t2)) && norm2(r0) <= res_tol2 * norm2(t3)) { converged = true; break; }
+    if (it == max_steps) break;
     cx<T> umb = u - b1;
     cx<T> j22 = v - b0;
     cx<T> j11 = j22 - u * umb;
     cx<T> j21 = -(v * umb);
     cx<T> det = j11 * j22 - umb * j21;
-    if (norm2(det) > T(0)) {
-      cx<T> idet = recip(det);
-      u = u + (r0 * umb - r1 * j22) * idet;
-      v = v + (r1 * j21 - r0 * j11) * idet;
+    if (!(norm2(det) > T(0))) break;
+    cx<T> idet = recip(det);
+    cx<T> du = (r0 * umb - r1 * j22) * idet;
+    cx<T> dv = (r1 * j21 - r0 * j11) * idet;
+    u = u + du;
+    v = v + dv;
+    if (norm2(du) + norm2(dv) <= step_tol2 * (norm2(u) + norm2(v))) {
+      converged = true;
+      b1 = c3 - u;
+      b0 = c2 - v - u * b1;
+      break;
     }
   }
-  b1 = c3 - u;
-  b0 = c2 - u * b1 - v;
+  return converged;
 }
 
-// charpoly -> start roots -> forward pair -> Bairstow polish of that quadratic factor
+// square root of y oriented forward: the reference's mode rule (waves.py:273-289) on the pair +-mu
+template <typename T> __device__ __forceinline__ cx<T> forward_sqrt(cx<T> y) {
+  cx<T> m = csqrt(y);
+  bool fwd = (ho_abs(m.im) > T(1e-9)) ? (m.im > T(0)) : (m.re > T(0));
+  return fwd ? m : -m;
+}
+
+// charpoly -> start values -> Bairstow polish of the forward quadratic factor.
+// Start values: when the odd coefficients are negligible (z is a principal axis of the rotated
+// tensors up to the reference's hidden 1e-8 angle offsets -- every un-tilted crystal) the quartic
+// is a perturbed biquadratic and the forward pair comes from three square roots; otherwise
+// Ferrari + classification.  A biquadratic start that fails to converge falls back to Ferrari.
 template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D) {
   cx<T> c3, c2, c1, c0;
   charpoly(D, c3, c2, c1, c0);
-  cx<T> lam[4];
-  start_roots(c3, c2, c1, c0, lam);
-  bool fwd[4];
-  classify(lam, fwd);
-  cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
+  const T tau4 = T(1e-20);
+  T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
+  bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
+  cx<T> u, v, b1, b0;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (biq) {
+      cx<T> y0, y1;
+      quad_roots(c2, c0, y0, y1);
+      cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
+      u = -(m0 + m1);
+      v = m0 * m1;
+    } else {
+      cx<T> lam[4];
+      start_roots(c3, c2, c1, c0, lam);
+      bool fwd[4];
+      classify(lam, fwd);
+      cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
+      for (int i = 0; i < 4; ++i) {
+        if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
+      }
+      u = -sf;
+      v = pf;
+    }
+    bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
+    if (ok || !biq) break;
+    biq = false;
   }
-  cx<T> u = -sf, v = pf, b1, b0;
-  bairstow(c3, c2, c1, c0, u, v, b1, b0);
   Spectrum<T> s;
   s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   return s;

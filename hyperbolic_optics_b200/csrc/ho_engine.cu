@@ -96,18 +96,19 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
       cx<T> w[4];
       if (L.kind == HO_ISO_EXIT) {
         exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
-      } else if (L.kind == HO_ANISO_EXIT) {
-        Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
-        Spectrum<T> s = split_spectrum(D);
-        substrate_plane(D, s, y0, y1);
-      } else {
+      } else if (L.kind == HO_ISO_FILM) {
         const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
         const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
-        if (L.kind == HO_ISO_FILM) {
-          iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
+        iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
+      } else {
+        // crystal film or crystal exit: one instance of the Delta assembly + spectral split
+        Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
+        Spectrum<T> s = split_spectrum(D);
+        if (L.kind == HO_ANISO_EXIT) {
+          substrate_plane(D, s, y0, y1);
         } else {
-          Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
-          Spectrum<T> s = split_spectrum(D);
+          const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
+          const cx<T> c = mk<T>(T(0), -(k0 * d));
           if (STABLE) film_stable(D, s, c, y0, y1, w);
           else film_transfer(D, s, c, y0, y1);
         }

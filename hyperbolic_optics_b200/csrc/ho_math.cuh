@@ -51,6 +51,8 @@ template <typename T> __device__ __forceinline__ cx<T> sel(bool c, cx<T> a, cx<T
 
 __device__ __forceinline__ double ho_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float ho_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double ho_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float ho_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double ho_cbrt(double x) { return cbrt(x); }
 __device__ __forceinline__ float ho_cbrt(float x) { return cbrtf(x); }
 __device__ __forceinline__ double ho_atan2(double y, double x) { return atan2(y, x); }
@@ -66,12 +68,16 @@ __device__ __forceinline__ float ho_copysign(float x, float y) { return copysign
 
 template <typename T> __device__ __forceinline__ T cabs(cx<T> a) { return ho_sqrt(norm2(a)); }
 
-// principal square root
+// principal square root.  Two reciprocal square roots instead of two square roots and a
+// division: t = sqrt(x) = x rsqrt(x) and 1/t = rsqrt(x) come from the same MUFU seed.
 template <typename T> __device__ __forceinline__ cx<T> csqrt(cx<T> z) {
-  T r = cabs(z);
-  if (r == T(0)) return mk<T>(T(0), T(0));
-  T t = ho_sqrt(T(0.5) * (r + ho_abs(z.re)));
-  T u = T(0.5) * z.im / t;
+  T n2 = norm2(z);
+  if (n2 == T(0)) return mk<T>(T(0), T(0));
+  T r = n2 * ho_rsqrt(n2);
+  T x = T(0.5) * (r + ho_abs(z.re));
+  T it = ho_rsqrt(x);
+  T t = x * it;
+  T u = (T(0.5) * z.im) * it;
   return (z.re >= T(0)) ? mk<T>(t, u) : mk<T>(ho_abs(u), ho_copysign(t, z.im));
 }
 

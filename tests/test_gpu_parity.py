@@ -242,14 +242,17 @@ def test_power_bookkeeping(name, backend, built_library):
             err = err[mask] if np.ndim(err) else err
             assert float(np.nanmax(err)) <= tol, f"{name}/{backend}/{key}: {float(np.nanmax(err)):.3e}"
         # R from fluxes == |r|^2 sums from amplitudes (reference tests/test_fields.py:57-95)
-        co, cross = ("r_pp", "r_sp") if pol == "p" else ("r_ss", "r_ps")
+        co, cross = ("r_pp", "r_ps") if pol == "p" else ("r_ss", "r_sp")  # r_{in -> out}
         r_amp = np.abs(getattr(s, co)) ** 2 + np.abs(getattr(s, cross)) ** 2
         with np.errstate(invalid="ignore"):
             diff = np.abs(np.asarray(summ["R"]) - r_amp)
-        fin = np.isfinite(diff)
         if backend == "scattering":
-            assert fin.all()
-        assert float(diff[fin].max()) <= (1e-9 if backend == "scattering" else 1e-5)
+            assert np.isfinite(diff).all()
+            assert float(diff.max()) <= 1e-9
+        else:  # the raw transfer product is only trusted on the reference's own trust region
+            dsub = parity.subsample(diff, fx["strides"])
+            dsub = dsub[mask] if np.ndim(dsub) else dsub
+            assert float(np.nanmax(dsub)) <= tol
         if backend == "scattering":
             assert summ["conservation_residual"] <= 1e-12
             # passivity (tests/test_fields.py:164-180): no layer generates power

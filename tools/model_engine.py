@@ -49,7 +49,7 @@ def run(plan, backend="transfer", stats=None, **kw):
                 continue
             if lp.kind == P.KIND_ANISO_EXIT:
                 D = layer_delta(plan, lp, f, a, b)
-                spec = am.split_spectrum(D, **kw)
+                spec = am.split_spectrum(D, stats=stats, **kw)
                 if stats is not None:
                     stats.setdefault("n_complex", []).append(spec[4])
                 Y = am.substrate_plane(D, spec[:4])
@@ -67,7 +67,7 @@ def run(plan, backend="transfer", stats=None, **kw):
                     Y = am.iso_film_transfer(k, eps, mu, Y, cfac)
             else:
                 D = layer_delta(plan, lp, f, a, b)
-                spec = am.split_spectrum(D, **kw)
+                spec = am.split_spectrum(D, stats=stats, **kw)
                 if stats is not None:
                     stats.setdefault("n_complex", []).append(spec[4])
                 if stable:
