@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -67,6 +68,105 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 #define HO_MIN_BLOCKS 2
 #endif
 
+// One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
+// the stable recursion (power bookkeeping only; dead code otherwise).
+template <typename T, bool STABLE, bool NM>
+__device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
+                                            ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4]) {
+  using namespace ho;
+  if (L.kind == HO_ISO_EXIT) {
+    exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
+  } else if (L.kind == HO_ISO_FILM) {
+    const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
+    const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
+    iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
+  } else {
+    // crystal film or crystal exit: one instance of the Delta assembly + spectral split
+    Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
+    Spectrum<T> s = split_spectrum(D);
+    if (L.kind == HO_ANISO_EXIT) {
+      substrate_plane(D, s, y0, y1);
+    } else {
+      const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
+      const cx<T> c = mk<T>(T(0), -(k0 * d));
+      if (STABLE) film_stable(D, s, c, y0, y1, w);
+      else film_transfer(D, s, c, y0, y1);
+    }
+  }
+}
+
+// Power planes of one point: [pol][R, T, A_0 .. A_{L-2}], pol 0 = p, 1 = s; interface fluxes
+// walk top -> bottom (reference fields.py:181-238).  Layers 0 .. n_upper-1 use the per-point
+// forms hf / maps wm; layers n_upper .. L-1 (thickness-sweep kernel only: the t-independent part
+// of the stack) use forms already composed into the coordinates at the top of layer n_upper,
+// `lower` = 4 doubles per layer.
+template <typename T, bool STABLE>
+__device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<T>& out, int64_t o, int a,
+                                           const ho::Vec4<T>& y0, const ho::Vec4<T>& y1,
+                                           const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower) {
+  using namespace ho;
+  const T inv_c = T(__ldg(P.prism_inv_cos + a)), inv_nc = T(__ldg(P.prism_inv_ncos + a));
+  cx<T> c0[2], c1[2];
+  incident_coords(y0, y1, inv_c, inv_nc, T(P.prism_inv_n), c0[0], c1[0], c0[1], c1[1]);
+  const T inv_sinc = T(2) * inv_nc;  // 1 / S_z^inc, S_z^inc = n cos(theta) / 2
+  const int n_planes = P.n_layers + 1;
+#pragma unroll
+  for (int pol = 0; pol < 2; ++pol) {
+    T* dst = out.power + (int64_t)pol * n_planes * out.power_stride + o;
+    cx<T> a0 = c0[pol], a1 = c1[pol];
+    T prev = flux_eval(hf[0], a0, a1);
+    dst[0] = T(1) - prev * inv_sinc;
+#pragma unroll 1
+    for (int l = 1; l < P.n_layers; ++l) {
+      if (STABLE && l <= n_upper) {  // through film l-1 (an upper layer, per-point map)
+        cx<T> b0 = fma(wm[l - 1][1], a1, wm[l - 1][0] * a0);
+        a1 = fma(wm[l - 1][3], a1, wm[l - 1][2] * a0);
+        a0 = b0;
+      }
+      T cur = (l < n_upper) ? flux_eval(hf[l], a0, a1) : flux_eval(lower + 4 * (l - n_upper), a0, a1);
+      dst[(int64_t)(1 + l) * out.power_stride] = (prev - cur) * inv_sinc;
+      prev = cur;
+    }
+    dst[out.power_stride] = prev * inv_sinc;
+  }
+}
+
+// r_ij, Mueller, Stokes (+ power) of one point from its top plane; stores at output offset o
+template <typename T, bool STABLE, bool POWER>
+__device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<T>& out, int64_t o, int a,
+                                           const ho::Vec4<T>& y0, const ho::Vec4<T>& y1,
+                                           const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower) {
+  using namespace ho;
+  cx<T> r_pp, r_ps, r_sp, r_ss;
+  reflect_from_plane(y0, y1, T(__ldg(P.prism_inv_cos + a)), T(__ldg(P.prism_inv_ncos + a)), T(P.prism_inv_n),
+                     r_pp, r_ps, r_sp, r_ss);
+  if constexpr (POWER) emit_power<T, STABLE>(P, out, o, a, y0, y1, hf, wm, n_upper, lower);
+  if (out.r_pp) out.r_pp[o] = r_pp;
+  if (out.r_ps) out.r_ps[o] = r_ps;
+  if (out.r_sp) out.r_sp[o] = r_sp;
+  if (out.r_ss) out.r_ss[o] = r_ss;
+  if (out.mueller || out.stokes) {
+    T M[16];
+    mueller_from_jones(r_pp, r_ps, r_sp, r_ss, M);
+    if (out.mueller) {
+      T* m = out.mueller + 16 * o;
+      if (sizeof(T) == 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) reinterpret_cast<double2*>(m)[i] = make_double2(M[2 * i], M[2 * i + 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(m)[i] = make_float4(M[4 * i], M[4 * i + 1], M[4 * i + 2], M[4 * i + 3]);
+      }
+    }
+    if (out.stokes) {
+      T* sv = out.stokes + 4 * o;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        sv[r] = M[4 * r] * out.s_in[0] + M[4 * r + 1] * out.s_in[1] + M[4 * r + 2] * out.s_in[2] + M[4 * r + 3] * out.s_in[3];
+    }
+  }
+}
+
 // NM: every crystal layer of the stack has mu proportional to the identity (all built-in
 // materials) -> sparser Berreman matrix; the general kernel handles full mu tensors.
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
@@ -92,89 +192,112 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
-      const ho_layer_t& L = P.layers[l];
       cx<T> w[4];
-      if (L.kind == HO_ISO_EXIT) {
-        exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
-      } else if (L.kind == HO_ISO_FILM) {
-        const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-        const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
-        iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
-      } else {
-        // crystal film or crystal exit: one instance of the Delta assembly + spectral split
-        Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
-        Spectrum<T> s = split_spectrum(D);
-        if (L.kind == HO_ANISO_EXIT) {
-          substrate_plane(D, s, y0, y1);
-        } else {
-          const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-          const cx<T> c = mk<T>(T(0), -(k0 * d));
-          if (STABLE) film_stable(D, s, c, y0, y1, w);
-          else film_transfer(D, s, c, y0, y1);
-        }
-      }
+      apply_layer<T, STABLE, NM>(P.layers[l], k, k0, f, a, b, t, y0, y1, w);
       if constexpr (POWER) {
         flux_form(y0, y1, hf[l]);
         if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
       }
     }
-
-    cx<T> r_pp, r_ps, r_sp, r_ss;
-    reflect_from_plane(y0, y1, T(__ldg(P.prism_inv_cos + a)), T(__ldg(P.prism_inv_ncos + a)), T(P.prism_inv_n),
-                       r_pp, r_ps, r_sp, r_ss);
-    const int64_t o = n - n_begin;
-    if constexpr (POWER) {
-      // planes [pol][R, T, A_0 .. A_{L-2}], pol 0 = p, 1 = s; fluxes walk top -> bottom
-      const T inv_c = T(__ldg(P.prism_inv_cos + a)), inv_nc = T(__ldg(P.prism_inv_ncos + a));
-      cx<T> c0[2], c1[2];
-      incident_coords(y0, y1, inv_c, inv_nc, T(P.prism_inv_n), c0[0], c1[0], c0[1], c1[1]);
-      const T inv_sinc = T(2) * inv_nc;  // 1 / S_z^inc, S_z^inc = n cos(theta) / 2
-      const int n_planes = P.n_layers + 1;
-#pragma unroll
-      for (int pol = 0; pol < 2; ++pol) {
-        T* dst = out.power + (int64_t)pol * n_planes * out.power_stride + o;
-        cx<T> a0 = c0[pol], a1 = c1[pol];
-        T prev = flux_eval(hf[0], a0, a1);
-        dst[0] = T(1) - prev * inv_sinc;
-#pragma unroll 1
-        for (int l = 1; l < P.n_layers; ++l) {
-          if constexpr (STABLE) {
-            cx<T> b0 = fma(wm[l - 1][1], a1, wm[l - 1][0] * a0);
-            a1 = fma(wm[l - 1][3], a1, wm[l - 1][2] * a0);
-            a0 = b0;
-          }
-          T cur = flux_eval(hf[l], a0, a1);
-          dst[(int64_t)(1 + l) * out.power_stride] = (prev - cur) * inv_sinc;
-          prev = cur;
-        }
-        dst[out.power_stride] = prev * inv_sinc;
-      }
-    }
-    if (out.r_pp) out.r_pp[o] = r_pp;
-    if (out.r_ps) out.r_ps[o] = r_ps;
-    if (out.r_sp) out.r_sp[o] = r_sp;
-    if (out.r_ss) out.r_ss[o] = r_ss;
-    if (out.mueller || out.stokes) {
-      T M[16];
-      mueller_from_jones(r_pp, r_ps, r_sp, r_ss, M);
-      if (out.mueller) {
-        T* m = out.mueller + 16 * o;
-        if (sizeof(T) == 8) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) reinterpret_cast<double2*>(m)[i] = make_double2(M[2 * i], M[2 * i + 1]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(m)[i] = make_float4(M[4 * i], M[4 * i + 1], M[4 * i + 2], M[4 * i + 3]);
-        }
-      }
-      if (out.stokes) {
-        T* sv = out.stokes + 4 * o;
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-          sv[r] = M[4 * r] * out.s_in[0] + M[4 * r + 1] * out.s_in[1] + M[4 * r + 2] * out.s_in[2] + M[4 * r + 3] * out.s_in[3];
-      }
-    }
+    emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, P.n_layers, nullptr);
   }
+}
+
+// ---- thickness axis (T > 1): warp-cooperative reuse of the t-independent part of the stack ----
+// Everything below the swept layer does not depend on t (reference waves.py:317-326).  A warp
+// owns `gpw` consecutive (f, a, b) groups = gpw*T consecutive points of the presentation order.
+//   pass 0    : lane <-> group.  Sweep the layers below the swept one, park the plane (and, for
+//               POWER, the flux forms of those layers composed into the coordinates at the top of
+//               that sub-stack) in shared memory: `row` doubles per group.
+//   pass 1..  : lane <-> point (32 consecutive points per pass: coalesced stores).  Fetch the
+//               group's plane from shared memory, apply the swept layer and the layers above it.
+// Both kinds of pass run through the same instance of the layer code (one loop body).
+constexpr int kSweepThreads = 128;
+
+template <bool STABLE, bool NM, bool POWER>
+__global__ void __launch_bounds__(kSweepThreads, 4)
+tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64_t n_begin, int64_t n_end,
+              int swept, int gpw, int row) {
+  using namespace ho;
+  typedef double T;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double* park = smem + (size_t)wib * gpw * row;
+  const int64_t g_first = n_begin / P.T, g_last = (n_end - 1) / P.T;  // inclusive
+  const int64_t n_units = (g_last - g_first + gpw) / gpw;
+  const int n_lower = P.n_layers - 1 - swept;
+  for (int64_t unit = (int64_t)blockIdx.x * wpb + wib; unit < n_units; unit += (int64_t)gridDim.x * wpb) {
+    const int64_t g0 = g_first + unit * gpw;
+    const int ng = (int)min((int64_t)gpw, g_last + 1 - g0);
+    const int64_t p_lo = max(n_begin, g0 * P.T), p_hi = min(n_end, (g0 + ng) * P.T);
+    const int n_pass = (int)((p_hi - p_lo + 31) / 32);
+#pragma unroll 1
+    for (int pass = 0; pass <= n_pass; ++pass) {
+      const int64_t n = p_lo + (int64_t)(pass - 1) * 32 + lane;
+      const bool active = pass == 0 ? lane < ng : n < p_hi;
+      if (active) {
+        int64_t q = pass == 0 ? g0 + lane : n / P.T;
+        const int t = pass == 0 ? 0 : (int)(n - q * P.T);
+        double* mine = park + (size_t)(q - g0) * row;
+        const int b = (int)(q % P.B); q /= P.B;
+        const int a = (int)(q % P.A);
+        const int f = (int)(q / P.A);
+        const T k = __ldg(P.kx + a), k0 = __ldg(P.k0 + f);
+        Vec4<T> y0, y1;
+        T hf[POWER ? HO_MAX_LAYERS : 1][4];
+        cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
+        int l_hi = P.n_layers - 1, l_lo = swept + 1;
+        if (pass > 0) {
+          l_hi = swept; l_lo = 0;
+          y0.v0 = mk(mine[0], mine[1]); y0.v1 = mk(mine[2], mine[3]); y0.v2 = mk(mine[4], mine[5]); y0.v3 = mk(mine[6], mine[7]);
+          y1.v0 = mk(mine[8], mine[9]); y1.v1 = mk(mine[10], mine[11]); y1.v2 = mk(mine[12], mine[13]); y1.v3 = mk(mine[14], mine[15]);
+        }
+#pragma unroll 1
+        for (int l = l_hi; l >= l_lo; --l) {
+          cx<T> w[4];
+          apply_layer<T, STABLE, NM>(P.layers[l], k, k0, f, a, b, t, y0, y1, w);
+          if constexpr (POWER) {
+            flux_form(y0, y1, hf[l]);
+            if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
+          }
+        }
+        if (pass == 0) {
+          mine[0] = y0.v0.re; mine[1] = y0.v0.im; mine[2] = y0.v1.re; mine[3] = y0.v1.im;
+          mine[4] = y0.v2.re; mine[5] = y0.v2.im; mine[6] = y0.v3.re; mine[7] = y0.v3.im;
+          mine[8] = y1.v0.re; mine[9] = y1.v0.im; mine[10] = y1.v1.re; mine[11] = y1.v1.im;
+          mine[12] = y1.v2.re; mine[13] = y1.v2.im; mine[14] = y1.v3.re; mine[15] = y1.v3.im;
+          if constexpr (POWER) {
+            // compose the lower forms into the coordinates at the top of layer swept+1:
+            // H'_l = M^H H_l M with M = W_{l-1} ... W_{swept+1}
+            cx<T> m00 = mk(1.0, 0.0), m01 = mk(0.0, 0.0), m10 = mk(0.0, 0.0), m11 = mk(1.0, 0.0);
+#pragma unroll 1
+            for (int l = swept + 1; l < P.n_layers; ++l) {
+              const T h0 = hf[l][0], h1 = hf[l][1];
+              const cx<T> h01 = mk(hf[l][2], hf[l][3]);
+              double* dst = mine + 16 + 4 * (l - swept - 1);
+              dst[0] = h0 * norm2(m00) + h1 * norm2(m10) + (cmulc(m10, m00) * h01).re;
+              dst[1] = h0 * norm2(m01) + h1 * norm2(m11) + (cmulc(m11, m01) * h01).re;
+              cx<T> x = (2.0 * h0) * cmulc(m01, m00) + (2.0 * h1) * cmulc(m11, m10) + cmulc(m11, m00) * h01
+                        + cmulc(m01, m10) * conj(h01);
+              dst[2] = x.re; dst[3] = x.im;
+              if constexpr (STABLE) {
+                if (l < P.n_layers - 1) {  // M <- W_l M
+                  cx<T> a00 = fma(wm[l][1], m10, wm[l][0] * m00), a01 = fma(wm[l][1], m11, wm[l][0] * m01);
+                  cx<T> a10 = fma(wm[l][3], m10, wm[l][2] * m00), a11 = fma(wm[l][3], m11, wm[l][2] * m01);
+                  m00 = a00; m01 = a01; m10 = a10; m11 = a11;
+                }
+              }
+            }
+          }
+        } else {
+          emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, swept + 1, mine + 16);
+        }
+      }
+      if (pass == 0) __syncwarp();
+    }
+    __syncwarp();  // the next unit's pass 0 overwrites the parked rows
+  }
+  (void)n_lower;
 }
 
 __global__ void fp64_peak_kernel(int iters, double* sink) {
@@ -239,11 +362,50 @@ int grid_for(int64_t n, const void* kernel) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// Thickness-axis launch: groups per warp as large as possible (reuse) while still leaving
+// enough warps to fill the device.  HO_B200_TSWEEP=0 (test hook) forces one thread per point,
+// HO_B200_TSWEEP_GPW=n forces the groups per warp.
+template <bool STABLE, bool NM, bool POWER>
+int launch_tsweep(const ho_problem_t* p, const OutPtrs<double>& out, int64_t n_begin, int64_t n_end, int swept,
+                  cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t groups = (n_end - 1) / p->T - n_begin / p->T + 1;
+  int gpw = 32;
+  while (gpw > 1 && groups / gpw < (int64_t)sms * 16) gpw >>= 1;
+  if (const char* env = getenv("HO_B200_TSWEEP_GPW")) {
+    int v = atoi(env);
+    if (v >= 1 && v <= 32) gpw = v;
+  }
+  int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) : 0);
+  row |= 1;  // odd row length: lane <-> row accesses in pass 0 are bank-conflict free
+  const int wpb = kSweepThreads / 32;
+  const size_t smem = (size_t)wpb * gpw * row * sizeof(double);
+  auto kern = tsweep_kernel<STABLE, NM, POWER>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSweepThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int64_t units = (groups + gpw - 1) / gpw;
+  int64_t want = (units + wpb - 1) / wpb, cap = (int64_t)sms * per_sm * 4;
+  const int grid = (int)(want < cap ? want : cap);
+  kern<<<grid, kSweepThreads, smem, stream>>>(*p, out, n_begin, n_end, swept, gpw, row);
+  return 0;
+}
+
 template <typename T, bool STABLE, bool NM, bool POWER>
 int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
+  if constexpr (sizeof(T) == 8) {
+    int swept = -1;
+    for (int l = 0; l < p->n_layers; ++l)
+      if (p->layers[l].n_thickness > 1) swept = l;
+    const char* env = getenv("HO_B200_TSWEEP");
+    if (p->T > 1 && swept >= 0 && !(env && atoi(env) == 0))
+      return launch_tsweep<STABLE, NM, POWER>(p, out, n_begin, n_end, swept, stream);
+  }
   const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER>;
-  int grid = grid_for(n_end - n_begin, kern);
-  reflect_kernel<T, STABLE, NM, POWER><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end);
+  reflect_kernel<T, STABLE, NM, POWER><<<grid_for(n_end - n_begin, kern), kThreads, 0, stream>>>(*p, out, n_begin, n_end);
   return 0;
 }
 

@@ -259,3 +259,36 @@ def test_power_bookkeeping(name, backend, built_library):
             for rec in summ["layers"]:
                 assert float(np.min(rec["absorptance"])) >= -1e-9
             assert float(np.min(summ["T"])) >= -1e-9
+
+
+@pytest.mark.parametrize("name", ["c5_thickness_11layer", "thickness_axis_film"])
+@pytest.mark.parametrize("gpw", ["1", "4", "32"])
+def test_thickness_axis_reuse_matches_point_per_thread(name, gpw, built_library, monkeypatch):
+    """The thickness-sweep kernel (the t-independent layers are swept once per (f, a, b) group by a
+    warp and reused for every thickness sample, reference waves.py:317-326) gives the same results
+    as one thread per point, for both backends, including sub-ranges that cut through a group."""
+    from hyperbolic_optics_b200 import engine
+    from hyperbolic_optics_b200.plan import build_plan
+    from hyperbolic_optics_b200.scenario import ScenarioSetup
+
+    sc, payload = parity.scenario_for(name, ScenarioSetup)
+    plan = build_plan(sc, payload["Layers"])
+    n = plan.n_points
+    planes = 2 * (len(plan.layers) + 1)
+    for backend in ("transfer", "scattering"):
+        prob = engine.DeviceProblem(plan, backend, "cuda:0")
+        monkeypatch.setenv("HO_B200_TSWEEP", "0")
+        ref = engine.DeviceOutputs(n, prob.device, power_planes=planes)
+        engine.reflect(prob, ref)
+        monkeypatch.setenv("HO_B200_TSWEEP", "1")
+        monkeypatch.setenv("HO_B200_TSWEEP_GPW", gpw)
+        for lo, hi in ((0, n), (5, n - 3), (n // 2 + 1, n // 2 + 2)):
+            got = engine.DeviceOutputs(hi - lo, prob.device, power_planes=planes)
+            engine.reflect(prob, got, lo, hi)
+            torch.cuda.synchronize()
+            for a, b in ((got.r, ref.r[:, lo:hi]), (got.mueller, ref.mueller[lo:hi]), (got.power, ref.power[:, lo:hi])):
+                a, b = torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b
+                fin = torch.isfinite(b)
+                assert torch.equal(torch.isfinite(a), fin)
+                scale = b[fin].abs().max().item() if fin.any() else 1.0
+                assert (a[fin] - b[fin]).abs().max().item() <= 1e-12 * max(scale, 1.0)
