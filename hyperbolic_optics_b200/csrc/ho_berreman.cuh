@@ -453,21 +453,21 @@ template <typename T, bool NM> __device__ __forceinline__ void film_stable(const
   w[2] = fma(n11, g0.v1, n10 * g0.v0); w[3] = fma(n11, g1.v1, n10 * g1.v0);
 }
 
-// Forward invariant subspace of a semi-infinite crystal: P_f [e0 e1].  With unit seeds the first
-// product D e_k is just a column of D, so each column costs two mat-vecs instead of three.
+// Forward invariant subspace of a semi-infinite crystal: q_b(D) [e0 e1], q_b(x) = x^2 - s_b x + p_b.
+// q_b(D) annihilates the backward subspace and is invertible on the forward one, so its columns
+// span the same plane as P_f [e0 e1] (r_*, the Mueller matrix and the flux ratios only depend on
+// the plane); D e_k is just column k of D, so each column costs one mat-vec.
 template <typename T, bool NM> __device__ __forceinline__ void substrate_plane(const Delta<T, NM>& D, const Spectrum<T>& s, Vec4<T>& y0, Vec4<T>& y1) {
-  cx<T> h0, h1;
-  projector_coeffs(s, h0, h1);
   const cx<T> zero = mk<T>(T(0), T(0));
-  Vec4<T> w;
+  Vec4<T> col;
   // column 0 of D is (a, 0, g, j)
-  w.v0 = fma(h1, D.a, h0); w.v1 = zero; w.v2 = h1 * D.g; w.v3 = h1 * D.j;
-  Vec4<T> t1 = matvec(D, w);
-  y0 = axpy(s.pb, w, axpy(-s.sb, t1, matvec(D, t1)));
+  col.v0 = D.a; col.v1 = zero; col.v2 = D.g; col.v3 = D.j;
+  y0 = axpy(-s.sb, col, matvec(D, col));
+  y0.v0 = y0.v0 + s.pb;
   // column 1 of D is (b, e, h, -g)
-  w.v0 = h1 * D.b; w.v1 = NM ? h0 : fma(h1, D.e, h0); w.v2 = h1 * D.h; w.v3 = -(h1 * D.g);
-  t1 = matvec(D, w);
-  y1 = axpy(s.pb, w, axpy(-s.sb, t1, matvec(D, t1)));
+  col.v0 = D.b; col.v1 = NM ? zero : D.e; col.v2 = D.h; col.v3 = -D.g;
+  y1 = axpy(-s.sb, col, matvec(D, col));
+  y1.v1 = y1.v1 + s.pb;
 }
 
 // ---- isotropic layers: D^2 = kz^2 I, closed forms (reference-equivalent) ----

@@ -42,6 +42,14 @@ template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p)
   return ho::mk<T>(T(v.x), T(v.y));
 }
 
+// Output stores are streaming (st.global.cs, evict-first): results are never re-read by the
+// kernel, so they must not push the threads' register-spill lines (which are re-used every few
+// hundred cycles) out of L2 -- without this the spills cost ~180 B/point of DRAM write-back.
+__device__ __forceinline__ void st_stream(ho::cx<double>* p, ho::cx<double> v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
+__device__ __forceinline__ void st_stream(ho::cx<float>* p, ho::cx<float> v) { __stcs(reinterpret_cast<float2*>(p), make_float2(v.re, v.im)); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
 template <typename T> __device__ __forceinline__ ho::Sym6<T> load_sym(const ho_c128* table, int row) {
   const ho_c128* p = table + 6 * (int64_t)row;
   ho::Sym6<T> s;
@@ -115,7 +123,7 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
     T* dst = out.power + (int64_t)pol * n_planes * out.power_stride + o;
     cx<T> a0 = c0[pol], a1 = c1[pol];
     T prev = flux_eval(hf[0], a0, a1);
-    dst[0] = T(1) - prev * inv_sinc;
+    st_stream(dst, T(1) - prev * inv_sinc);
 #pragma unroll 1
     for (int l = 1; l < P.n_layers; ++l) {
       if (STABLE && l <= n_upper) {  // through film l-1 (an upper layer, per-point map)
@@ -124,10 +132,10 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
         a0 = b0;
       }
       T cur = (l < n_upper) ? flux_eval(hf[l], a0, a1) : flux_eval(lower + 4 * (l - n_upper), a0, a1);
-      dst[(int64_t)(1 + l) * out.power_stride] = (prev - cur) * inv_sinc;
+      st_stream(dst + (int64_t)(1 + l) * out.power_stride, (prev - cur) * inv_sinc);
       prev = cur;
     }
-    dst[out.power_stride] = prev * inv_sinc;
+    st_stream(dst + out.power_stride, prev * inv_sinc);
   }
 }
 
@@ -141,10 +149,10 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
   reflect_from_plane(y0, y1, T(__ldg(P.prism_inv_cos + a)), T(__ldg(P.prism_inv_ncos + a)), T(P.prism_inv_n),
                      r_pp, r_ps, r_sp, r_ss);
   if constexpr (POWER) emit_power<T, STABLE>(P, out, o, a, y0, y1, hf, wm, n_upper, lower);
-  if (out.r_pp) out.r_pp[o] = r_pp;
-  if (out.r_ps) out.r_ps[o] = r_ps;
-  if (out.r_sp) out.r_sp[o] = r_sp;
-  if (out.r_ss) out.r_ss[o] = r_ss;
+  if (out.r_pp) st_stream(out.r_pp + o, r_pp);
+  if (out.r_ps) st_stream(out.r_ps + o, r_ps);
+  if (out.r_sp) st_stream(out.r_sp + o, r_sp);
+  if (out.r_ss) st_stream(out.r_ss + o, r_ss);
   if (out.mueller || out.stokes) {
     T M[16];
     mueller_from_jones(r_pp, r_ps, r_sp, r_ss, M);
@@ -152,17 +160,17 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
       T* m = out.mueller + 16 * o;
       if (sizeof(T) == 8) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) reinterpret_cast<double2*>(m)[i] = make_double2(M[2 * i], M[2 * i + 1]);
+        for (int i = 0; i < 8; ++i) __stcs(reinterpret_cast<double2*>(m) + i, make_double2(M[2 * i], M[2 * i + 1]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(m)[i] = make_float4(M[4 * i], M[4 * i + 1], M[4 * i + 2], M[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) __stcs(reinterpret_cast<float4*>(m) + i, make_float4(M[4 * i], M[4 * i + 1], M[4 * i + 2], M[4 * i + 3]));
       }
     }
     if (out.stokes) {
       T* sv = out.stokes + 4 * o;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        sv[r] = M[4 * r] * out.s_in[0] + M[4 * r + 1] * out.s_in[1] + M[4 * r + 2] * out.s_in[2] + M[4 * r + 3] * out.s_in[3];
+        st_stream(sv + r, M[4 * r] * out.s_in[0] + M[4 * r + 1] * out.s_in[1] + M[4 * r + 2] * out.s_in[2] + M[4 * r + 3] * out.s_in[3]);
     }
   }
 }

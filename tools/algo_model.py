@@ -470,15 +470,18 @@ def film_stable(D, Y, spec, cfac, rows=(0, 1), return_w=False):
 
 
 def substrate_plane(D, spec):
-    """Basis of the forward invariant subspace: P_f [e0 e1]."""
+    """Basis of the forward invariant subspace: q_b(D) [e0 e1] = (D^2 - s_b D + p_b I) [e0 e1].
+
+    q_b(D) annihilates the backward subspace and is invertible on the forward one, so its columns
+    span the same plane as P_f [e0 e1] (r_* only depend on the plane) at one
+    mat-vec per column: D e_k is just column k of D."""
+    a, b, c, d, e, f, g, h, j = D
     sf, pf, sb, pb = spec
-    one = np.ones_like(sf)
     zero = np.zeros_like(sf)
     cols = []
-    for idx in range(2):
-        y = tuple(one if i == idx else zero for i in range(4))
-        z, _ = project_forward(D, y, sf, pf, sb, pb)
-        cols.append(z)
+    for idx, col in enumerate(((a, zero, g, j), (b, e, h, -g))):
+        t1 = matvec(D, col)
+        cols.append(tuple(t1[i] - sb * col[i] + (pb if i == idx else 0.0) for i in range(4)))
     return cols
 
 
