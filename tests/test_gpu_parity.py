@@ -292,3 +292,41 @@ def test_thickness_axis_reuse_matches_point_per_thread(name, gpw, built_library,
                 assert torch.equal(torch.isfinite(a), fin)
                 scale = b[fin].abs().max().item() if fin.any() else 1.0
                 assert (a[fin] - b[fin]).abs().max().item() <= 1e-12 * max(scale, 1.0)
+
+
+def test_c4_full_size_properties(built_library):
+    """BASELINE config 4 at its full size (410 x 512 x 480 = 1.0076e8 points), results kept in HBM:
+    size-independent properties instead of an oracle run -- the transfer and the stable recursion
+    (independent algorithms) agree to 1e-10 Jones-relative at every point, reflection is passive,
+    M00 of the fused Mueller matrix equals half the summed |r|^2, and the whole grid is finite."""
+    import bench
+    from hyperbolic_optics_b200 import engine
+    from hyperbolic_optics_b200.plan import build_plan
+    from hyperbolic_optics_b200.scenario import ScenarioSetup
+
+    payload = bench.c4_payload(bench.F_PER_GPU)
+    sc = ScenarioSetup(payload["ScenarioData"], n_incident=bench.N_INC, n_azimuthal=bench.N_AZ)
+    plan = build_plan(sc, payload["Layers"])
+    n = plan.n_points
+    assert n == 100761600
+    res = {}
+    for backend in ("transfer", "scattering"):
+        prob = engine.DeviceProblem(plan, backend, "cuda:0")
+        out = engine.DeviceOutputs(n, prob.device)
+        engine.reflect(prob, out)
+        res[backend] = out
+    torch.cuda.synchronize()
+    t, s = res["transfer"], res["scattering"]
+    assert bool(torch.isfinite(torch.view_as_real(s.r)).all()) and bool(torch.isfinite(torch.view_as_real(t.r)).all())
+    num = (t.r - s.r).abs().square().sum(dim=0)
+    den = s.r.abs().square().sum(dim=0)
+    assert float((num / den).max().sqrt()) <= 1e-10
+    refl_p = s.r[0].abs().square() + s.r[1].abs().square()   # |r_pp|^2 + |r_ps|^2
+    refl_s = s.r[3].abs().square() + s.r[2].abs().square()
+    assert float(refl_p.max()) <= 1.0 + 1e-9 and float(refl_s.max()) <= 1.0 + 1e-9
+    m00 = 0.5 * den
+    assert float((s.mueller[:, 0, 0] - m00).abs().max()) <= 1e-12
+    # both layers are invariant under rotation about z (hBN c-axis along z, SiC isotropic): the
+    # result cannot depend on the azimuth
+    r = s.r.reshape(4, bench.F_PER_GPU, bench.N_INC, bench.N_AZ)
+    assert float((r - r[..., :1]).abs().max()) <= 1e-9
