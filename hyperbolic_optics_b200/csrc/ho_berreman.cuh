@@ -20,6 +20,9 @@ template <typename T> struct Vec4 { cx<T> v0, v1, v2, v3; };
 template <typename T> struct Sym6 { cx<T> xx, xy, xz, yy, yz, zz; };
 // sums / products of the forward and backward root pairs
 template <typename T> struct Spectrum { cx<T> sf, pf, sb, pb; };
+// z rows of the rotated tensors, for the longitudinal fields of a mode (reference waves.py:382-408):
+// Ez = -(k Hy + e20 Ex + e21 Ey) / e22,  Hz = (k Ey - m20 Hx - m21 Hy) / m22
+template <typename T> struct ZRow { cx<T> e20, e21, ie22, m20, m21, im22; };
 
 template <typename T> __device__ __forceinline__ Vec4<T> axpy(cx<T> s, const Vec4<T>& x, const Vec4<T>& y) {
   Vec4<T> r; r.v0 = fma(s, x.v0, y.v0); r.v1 = fma(s, x.v1, y.v1); r.v2 = fma(s, x.v2, y.v2); r.v3 = fma(s, x.v3, y.v3); return r;
@@ -57,8 +60,9 @@ template <typename T> __device__ __forceinline__ Sym6<T> rotate_z(const Sym6<T>&
 }
 
 // scalar-mu flavour: m = mu * I
-template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k, const Sym6<T>& e, cx<T> mu) {
+template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k, const Sym6<T>& e, cx<T> mu, ZRow<T>& z) {
   cx<T> ie = recip(e.zz), im = recip(mu);
+  z.e20 = e.xz; z.e21 = e.yz; z.ie22 = ie; z.m20 = mk<T>(T(0), T(0)); z.m21 = z.m20; z.im22 = im;
   T k2 = k * k;
   Delta<T, true> D;
   D.a = -(k * (e.xz * ie));
@@ -73,8 +77,9 @@ template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k,
   return D;
 }
 
-template <typename T> __device__ __forceinline__ Delta<T> berreman(T k, const Sym6<T>& e, const Sym6<T>& m) {
+template <typename T> __device__ __forceinline__ Delta<T> berreman(T k, const Sym6<T>& e, const Sym6<T>& m, ZRow<T>& z) {
   cx<T> ie = recip(e.zz), im = recip(m.zz);
+  z.e20 = e.xz; z.e21 = e.yz; z.ie22 = ie; z.m20 = m.xz; z.m21 = m.yz; z.im22 = im;
   T k2 = k * k;
   Delta<T> D;
   D.a = -(k * (e.xz * ie));
@@ -560,6 +565,68 @@ template <typename T> __device__ __forceinline__ void incident_coords(const Vec4
   cx<T> idet = recip(g00 * g22 - g02 * g20);
   cp0 = -(g02 * idet); cp1 = g00 * idet;   // (a_s, a_p) = (0, 1)
   cs0 = g22 * idet;    cs1 = -(g20 * idet);  // (a_s, a_p) = (1, 0)
+}
+
+// ---- transmission coefficients: the reference's mode basis of a crystal exit ----
+// LAPACK zgeev convention (what numpy.linalg.eig returns, reference waves.py:270): unit 2-norm,
+// the component of largest modulus (first on ties) real positive.
+template <typename T> __device__ __forceinline__ Vec4<T> lapack_normalise(const Vec4<T>& v) {
+  T n0 = norm2(v.v0), n1 = norm2(v.v1), n2 = norm2(v.v2), n3 = norm2(v.v3);
+  T inv = ho_rsqrt(n0 + n1 + n2 + n3);
+  cx<T> big = v.v0; T nb = n0;
+  if (n1 > nb) { big = v.v1; nb = n1; }
+  if (n2 > nb) { big = v.v2; nb = n2; }
+  if (n3 > nb) { big = v.v3; nb = n3; }
+  cx<T> ph = (inv * ho_rsqrt(nb)) * conj(big);  // unit phase / norm
+  return scale(ph, v);
+}
+
+// p-likeness measures of a mode (reference waves.py:382-408, 490-497): complex Poynting E x H
+// (no conjugate) and the electric field
+template <typename T> __device__ __forceinline__ void mode_character(const Vec4<T>& v, const ZRow<T>& z, T k, T& cp, T& ce) {
+  cx<T> ez = -((k * v.v3 + z.e20 * v.v0 + z.e21 * v.v1) * z.ie22);
+  cx<T> hz = (k * v.v1 - z.m20 * v.v2 - z.m21 * v.v3) * z.im22;
+  T px = norm2(v.v1 * hz - ez * v.v3), py = norm2(ez * v.v2 - v.v0 * hz);
+  T ex = norm2(v.v0), ey = norm2(v.v1);
+  cp = px / (px + py);
+  ce = ex / (ex + ey);
+}
+
+// binv (row-major 2x2): coordinates in the kernel's forward-plane basis [y0 y1] -> amplitudes of
+// the reference's exit modes (t0, t1) = eigenvectors in LAPACK normalisation, ordered by
+// sort_poynting_indices (waves.py:474-510).  Degenerate forward pair (isotropic crystal): the
+// reference's basis is whatever LAPACK returns for a 2-dimensional eigenspace -- not reproducible;
+// the kernel basis normalised to unit E rows is used instead (binv = L [y0 y1]).
+template <typename T, bool NM> __device__ __forceinline__ void exit_mode_basis(const Delta<T, NM>& D, const Spectrum<T>& s, const ZRow<T>& z, T k,
+                                                                          const Vec4<T>& y0, const Vec4<T>& y1, cx<T> binv[4]) {
+  cx<T> l0, l1;
+  quad_roots(-s.sf, s.pf, l0, l1);
+  cx<T> n00, n01, n10, n11;
+  if (norm2(l0 - l1) <= T(1e-20) * (norm2(l0) + norm2(l1))) {
+    binv[0] = y0.v0; binv[1] = y1.v0; binv[2] = y0.v1; binv[3] = y1.v1;
+    return;
+  }
+  Vec4<T> dy0 = matvec(D, y0), dy1 = matvec(D, y1);
+  // eigenvector of l0: (D - l1) y, of l1: (D - l0) y; take the better-conditioned seed column
+  Vec4<T> a0 = axpy(-l1, y0, dy0), a1 = axpy(-l1, y1, dy1);
+  Vec4<T> b0 = axpy(-l0, y0, dy0), b1 = axpy(-l0, y1, dy1);
+  Vec4<T> u = lapack_normalise(sel(norm2(a0) >= norm2(a1), a0, a1));
+  Vec4<T> v = lapack_normalise(sel(norm2(b0) >= norm2(b1), b0, b1));
+  T cpu_, ceu, cpv, cev;
+  mode_character(u, z, k, cpu_, ceu);
+  mode_character(v, z, k, cpv, cev);
+  // order: larger C_P first when they differ by more than 1e-6, else smaller C_E first; the
+  // reference's incoming order is Im(lambda) descending (ties keep that order)
+  bool u_first_in = l0.im >= l1.im;
+  bool swap;
+  if (ho_abs(cpu_ - cpv) > T(1e-6)) swap = cpv > cpu_;
+  else swap = (cev < ceu) || (cev == ceu && !u_first_in);
+  Vec4<T> t0 = sel(swap, v, u), t1 = sel(swap, u, v);
+  // B = (L Y)^-1 L [t0 t1], binv = B^-1
+  inv2(y0.v0, y1.v0, y0.v1, y1.v1, n00, n01, n10, n11);
+  cx<T> b00 = fma(n01, t0.v1, n00 * t0.v0), b01 = fma(n01, t1.v1, n00 * t1.v0);
+  cx<T> b10 = fma(n11, t0.v1, n10 * t0.v0), b11 = fma(n11, t1.v1, n10 * t1.v0);
+  inv2(b00, b01, b10, b11, binv[0], binv[1], binv[2], binv[3]);
 }
 
 // Mueller matrix M = Re(A F A^-1), F = J (x) J* in the reference's layout (mueller.py:266-307)

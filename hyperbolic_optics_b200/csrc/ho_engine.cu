@@ -35,6 +35,7 @@ template <typename T> struct OutPtrs {
   T* mueller; T* stokes;
   T s_in[4];
   T* power; int64_t power_stride;
+  ho::cx<T>* t_pp; ho::cx<T>* t_ps; ho::cx<T>* t_sp; ho::cx<T>* t_ss;
 };
 
 template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p) {
@@ -58,17 +59,17 @@ template <typename T> __device__ __forceinline__ ho::Sym6<T> load_sym(const ho_c
   return s;
 }
 
-template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer_delta(const ho_layer_t& L, T k, int f, int b) {
+template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer_delta(const ho_layer_t& L, T k, int f, int b, ho::ZRow<T>& z) {
   using namespace ho;
   int bi = L.n_beta > 1 ? b : 0;
   T cb = T(__ldg(L.cos_beta + bi)), sb = T(__ldg(L.sin_beta + bi));
   Sym6<T> e = rotate_z(load_sym<T>(L.eps, L.n_eps > 1 ? f : 0), cb, sb);
   if constexpr (NM) {
-    return berreman_nm(k, e, ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0)));
+    return berreman_nm(k, e, ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0)), z);
   } else {
     Sym6<T> m = load_sym<T>(L.mu, L.n_mu > 1 ? f : 0);
     if (!L.mu_scalar) m = rotate_z(m, cb, sb);
-    return berreman(k, e, m);
+    return berreman(k, e, m, z);
   }
 }
 
@@ -78,22 +79,26 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
 // the stable recursion (power bookkeeping only; dead code otherwise).
-template <typename T, bool STABLE, bool NM>
+// binv (EXTRAS): kernel exit basis -> the reference's exit-mode amplitudes (transmission coefficients).
+template <typename T, bool STABLE, bool NM, bool EXTRAS>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
-                                            ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4]) {
+                                            ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4]) {
   using namespace ho;
   if (L.kind == HO_ISO_EXIT) {
     exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
+    if constexpr (EXTRAS) { binv[0] = mk<T>(T(1), T(0)); binv[1] = mk<T>(T(0), T(0)); binv[2] = binv[1]; binv[3] = binv[0]; }
   } else if (L.kind == HO_ISO_FILM) {
     const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
     const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
     iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
   } else {
     // crystal film or crystal exit: one instance of the Delta assembly + spectral split
-    Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b);
+    ZRow<T> z;
+    Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
     Spectrum<T> s = split_spectrum(D);
     if (L.kind == HO_ANISO_EXIT) {
       substrate_plane(D, s, y0, y1);
+      if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
     } else {
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       const cx<T> c = mk<T>(T(0), -(k0 * d));
@@ -111,19 +116,21 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
 template <typename T, bool STABLE>
 __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<T>& out, int64_t o, int a,
                                            const ho::Vec4<T>& y0, const ho::Vec4<T>& y1,
-                                           const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower) {
+                                           const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower,
+                                           const ho::cx<T>* binv, bool crystal_exit) {
   using namespace ho;
   const T inv_c = T(__ldg(P.prism_inv_cos + a)), inv_nc = T(__ldg(P.prism_inv_ncos + a));
   cx<T> c0[2], c1[2];
   incident_coords(y0, y1, inv_c, inv_nc, T(P.prism_inv_n), c0[0], c1[0], c0[1], c1[1]);
   const T inv_sinc = T(2) * inv_nc;  // 1 / S_z^inc, S_z^inc = n cos(theta) / 2
   const int n_planes = P.n_layers + 1;
+  const bool want_power = out.power != nullptr;
 #pragma unroll
   for (int pol = 0; pol < 2; ++pol) {
     T* dst = out.power + (int64_t)pol * n_planes * out.power_stride + o;
     cx<T> a0 = c0[pol], a1 = c1[pol];
     T prev = flux_eval(hf[0], a0, a1);
-    st_stream(dst, T(1) - prev * inv_sinc);
+    if (want_power) st_stream(dst, T(1) - prev * inv_sinc);
 #pragma unroll 1
     for (int l = 1; l < P.n_layers; ++l) {
       if (STABLE && l <= n_upper) {  // through film l-1 (an upper layer, per-point map)
@@ -132,10 +139,20 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
         a0 = b0;
       }
       T cur = (l < n_upper) ? flux_eval(hf[l], a0, a1) : flux_eval(lower + 4 * (l - n_upper), a0, a1);
-      st_stream(dst + (int64_t)(1 + l) * out.power_stride, (prev - cur) * inv_sinc);
+      if (want_power) st_stream(dst + (int64_t)(1 + l) * out.power_stride, (prev - cur) * inv_sinc);
       prev = cur;
     }
-    st_stream(dst + out.power_stride, prev * inv_sinc);
+    if (want_power) st_stream(dst + out.power_stride, prev * inv_sinc);
+    if (out.t_pp) {
+      // (a0, a1): coordinates at the exit in the kernel basis.  Thickness-sweep kernel, stable
+      // recursion: the maps below the swept layer were folded into the parked data (lower[-8..-1]).
+      cx<T> e0 = fma(binv[1], a1, binv[0] * a0), e1 = fma(binv[3], a1, binv[2] * a0);
+      // transfer: t_{in -> out} in Gamma's (col 0, col 2) slots (structure.py:340-347);
+      // scattering with a crystal exit: S-matrix picks in mode order (scattering.py:155-164)
+      const bool smat = STABLE && crystal_exit;
+      if (pol == 0) { st_stream((smat ? out.t_pp : out.t_ps) + o, e0); st_stream((smat ? out.t_ps : out.t_pp) + o, e1); }
+      else          { st_stream((smat ? out.t_sp : out.t_ss) + o, e0); st_stream((smat ? out.t_ss : out.t_sp) + o, e1); }
+    }
   }
 }
 
@@ -143,12 +160,14 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
 template <typename T, bool STABLE, bool POWER>
 __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<T>& out, int64_t o, int a,
                                            const ho::Vec4<T>& y0, const ho::Vec4<T>& y1,
-                                           const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower) {
+                                           const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower,
+                                           const ho::cx<T>* binv) {
   using namespace ho;
   cx<T> r_pp, r_ps, r_sp, r_ss;
   reflect_from_plane(y0, y1, T(__ldg(P.prism_inv_cos + a)), T(__ldg(P.prism_inv_ncos + a)), T(P.prism_inv_n),
                      r_pp, r_ps, r_sp, r_ss);
-  if constexpr (POWER) emit_power<T, STABLE>(P, out, o, a, y0, y1, hf, wm, n_upper, lower);
+  if constexpr (POWER)
+    emit_power<T, STABLE>(P, out, o, a, y0, y1, hf, wm, n_upper, lower, binv, P.layers[P.n_layers - 1].kind == HO_ANISO_EXIT);
   if (out.r_pp) st_stream(out.r_pp + o, r_pp);
   if (out.r_ps) st_stream(out.r_ps + o, r_ps);
   if (out.r_sp) st_stream(out.r_sp + o, r_sp);
@@ -198,16 +217,17 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     // recursion, the coordinate map through every film
     T hf[POWER ? HO_MAX_LAYERS : 1][4];
     cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
+    cx<T> binv[4];
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
       cx<T> w[4];
-      apply_layer<T, STABLE, NM>(P.layers[l], k, k0, f, a, b, t, y0, y1, w);
+      apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv);
       if constexpr (POWER) {
         flux_form(y0, y1, hf[l]);
         if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
       }
     }
-    emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, P.n_layers, nullptr);
+    emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, P.n_layers, nullptr, binv);
   }
 }
 
@@ -216,7 +236,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
 // owns `gpw` consecutive (f, a, b) groups = gpw*T consecutive points of the presentation order.
 //   pass 0    : lane <-> group.  Sweep the layers below the swept one, park the plane (and, for
 //               POWER, the flux forms of those layers composed into the coordinates at the top of
-//               that sub-stack) in shared memory: `row` doubles per group.
+//               that sub-stack, and the exit-mode map) in shared memory: `row` doubles per group.
 //   pass 1..  : lane <-> point (32 consecutive points per pass: coalesced stores).  Fetch the
 //               group's plane from shared memory, apply the swept layer and the layers above it.
 // Both kinds of pass run through the same instance of the layer code (one loop body).
@@ -254,6 +274,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
         Vec4<T> y0, y1;
         T hf[POWER ? HO_MAX_LAYERS : 1][4];
         cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
+        cx<T> binv[4];
         int l_hi = P.n_layers - 1, l_lo = swept + 1;
         if (pass > 0) {
           l_hi = swept; l_lo = 0;
@@ -263,7 +284,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
 #pragma unroll 1
         for (int l = l_hi; l >= l_lo; --l) {
           cx<T> w[4];
-          apply_layer<T, STABLE, NM>(P.layers[l], k, k0, f, a, b, t, y0, y1, w);
+          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv);
           if constexpr (POWER) {
             flux_form(y0, y1, hf[l]);
             if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
@@ -296,16 +317,21 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
                 }
               }
             }
+            // exit-mode map folded with the lower maps: coordinates at the top of layer swept+1
+            // -> reference exit-mode amplitudes
+            cx<T>* pb = reinterpret_cast<cx<T>*>(mine + 16 + 4 * n_lower);
+            pb[0] = fma(binv[1], m10, binv[0] * m00); pb[1] = fma(binv[1], m11, binv[0] * m01);
+            pb[2] = fma(binv[3], m10, binv[2] * m00); pb[3] = fma(binv[3], m11, binv[2] * m01);
           }
         } else {
-          emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, swept + 1, mine + 16);
+          emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, swept + 1, mine + 16,
+                                       reinterpret_cast<const cx<T>*>(mine + 16 + 4 * n_lower));
         }
       }
       if (pass == 0) __syncwarp();
     }
     __syncwarp();  // the next unit's pass 0 overwrites the parked rows
   }
-  (void)n_lower;
 }
 
 __global__ void fp64_peak_kernel(int iters, double* sink) {
@@ -386,7 +412,7 @@ int launch_tsweep(const ho_problem_t* p, const OutPtrs<double>& out, int64_t n_b
     int v = atoi(env);
     if (v >= 1 && v <= 32) gpw = v;
   }
-  int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) : 0);
+  int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) + 8 : 0);
   row |= 1;  // odd row length: lane <-> row accesses in pass 0 are bank-conflict free
   const int wpb = kSweepThreads / 32;
   const size_t smem = (size_t)wpb * gpw * row * sizeof(double);
@@ -420,7 +446,7 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
 template <typename T, bool STABLE, bool NM>
 int launch_nm(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
   if constexpr (sizeof(T) == 8) {
-    if (out.power) return launch_k<T, STABLE, NM, true>(p, out, n_begin, n_end, stream);
+    if (out.power || out.t_pp) return launch_k<T, STABLE, NM, true>(p, out, n_begin, n_end, stream);
   }
   return launch_k<T, STABLE, NM, false>(p, out, n_begin, n_end, stream);
 }
@@ -457,6 +483,12 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
   for (int i = 0; i < 4; ++i) o.s_in[i] = out->incident_stokes[i];
   o.power = out->power;
   o.power_stride = out->power_stride;
+  o.t_pp = reinterpret_cast<ho::cx<double>*>(out->t_pp);
+  o.t_ps = reinterpret_cast<ho::cx<double>*>(out->t_ps);
+  o.t_sp = reinterpret_cast<ho::cx<double>*>(out->t_sp);
+  o.t_ss = reinterpret_cast<ho::cx<double>*>(out->t_ss);
+  if ((o.t_pp || o.t_ps || o.t_sp || o.t_ss) && !(o.t_pp && o.t_ps && o.t_sp && o.t_ss))
+    return fail(HO_ERR_BAD_ARGUMENT, "t_pp, t_ps, t_sp, t_ss must be given together");
   if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<double, true>(problem, o, n_begin, n_end, s)
@@ -477,6 +509,7 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   for (int i = 0; i < 4; ++i) o.s_in[i] = 0.f;
   o.power = nullptr;
   o.power_stride = 0;
+  o.t_pp = o.t_ps = o.t_sp = o.t_ss = nullptr;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, n_begin, n_end, s)
                                                    : launch<float, false>(problem, o, n_begin, n_end, s);

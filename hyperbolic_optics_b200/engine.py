@@ -99,7 +99,8 @@ class DeviceProblem:
 class DeviceOutputs:
     """Caller-owned output buffers for a contiguous range of batch points."""
 
-    def __init__(self, n, device, mueller=True, stokes=None, dtype=torch.complex128, power_planes=0):
+    def __init__(self, n, device, mueller=True, stokes=None, dtype=torch.complex128, power_planes=0,
+                 transmission=False):
         self.n = n
         self.dtype = dtype
         real = torch.float64 if dtype == torch.complex128 else torch.float32
@@ -109,11 +110,12 @@ class DeviceOutputs:
         self.incident_stokes = stokes
         # power bookkeeping planes [2 * (n_layers + 1)][n]: per polarisation R, T, A_0 .. A_{L-2}
         self.power = torch.empty((power_planes, n), dtype=real, device=device) if power_planes else None
+        self.t = torch.empty((4, n), dtype=dtype, device=device) if transmission else None  # rows: pp, ps, sp, ss
 
     @property
     def nbytes(self):
         total = self.r.numel() * self.r.element_size()
-        for t in (self.mueller, self.stokes, self.power):
+        for t in (self.mueller, self.stokes, self.power, self.t):
             if t is not None:
                 total += t.numel() * t.element_size()
         return total
@@ -137,6 +139,8 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
             if out.power.shape[0] != 2 * (len(problem.plan.layers) + 1):
                 raise ValueError("power buffer must have 2 * (n_layers + 1) planes")
             o.power, o.power_stride = out.power.data_ptr(), out.power.shape[1]
+        if out.t is not None:
+            o.t_pp, o.t_ps, o.t_sp, o.t_ss = (out.t[i].data_ptr() for i in range(4))
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:
         o = nat.OutputsF32()

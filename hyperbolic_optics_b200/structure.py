@@ -68,6 +68,7 @@ class Structure:
         self.chunk_points = int(chunk_points)
         self.with_mueller = True
         self.with_power = False
+        self.with_transmission = False
         self.power = None
         self.incident_stokes = None
         self.keep_on_device = False
@@ -77,6 +78,7 @@ class Structure:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._backend = "transfer"
+        self._last_backend = "transfer"
 
     # -- staged protocol ---------------------------------------------------------------
     def get_scenario(self, scenario_data):
@@ -108,17 +110,24 @@ class Structure:
         self._run("scattering")
 
     def calculate_transmissivity(self):
-        raise NotImplementedError(
-            "t_* for the GPU engine is not available yet (needs LAPACK-convention eigenvectors "
-            "for a crystal exit; see DESIGN.md 'next').")
+        """``t_pp, t_ps, t_sp, t_ss`` (reference ``structure.py:326-347``).  The reference derives
+        them from the stored transfer matrix; here the kernel is re-launched with the transmission
+        outputs enabled (the plan is kept, so this costs one launch).  ``execute(...,
+        transmission=True)`` produces them in the first launch instead."""
+        if self.plan is None:
+            raise ValueError("Structure has not been executed; call structure.execute(payload).")
+        if self.t_pp is None:
+            self.with_transmission = True
+            self._run(self._last_backend)
 
     # -- one-call protocol ---------------------------------------------------------------
     def execute(self, payload, backend="transfer", mueller=True, incident_stokes=None,
-                keep_on_device=False, own_results=None, power=False):
+                keep_on_device=False, own_results=None, power=False, transmission=False):
         if backend not in ("transfer", "scattering"):
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
         self.with_mueller = bool(mueller)
         self.with_power = bool(power)
+        self.with_transmission = bool(transmission)
         self.incident_stokes = incident_stokes
         self.keep_on_device = bool(keep_on_device)
         if own_results is not None:
@@ -129,6 +138,7 @@ class Structure:
 
     # -- device run ------------------------------------------------------------------------
     def _run(self, backend):
+        self._last_backend = backend
         plan = self.plan
         prob = engine.DeviceProblem(plan, backend, self.device)
         self.h2d_bytes = prob.h2d_bytes
@@ -137,10 +147,11 @@ class Structure:
         want_stokes = self.incident_stokes is not None
         planes = 2 * (len(plan.layers) + 1) if self.with_power else 0
         if self.keep_on_device:
-            out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes)
+            out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
+                                       transmission=self.with_transmission)
             engine.reflect(prob, out)
             r = out.r.reshape((4,) + shape)
-            self._assign(r, out.mueller, out.stokes, out.power, shape, to_numpy=False)
+            self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False)
             self.d2h_bytes = 0
             return
         # host results: kernel -> device chunk (double buffered) -> pinned host, D2H on a copy stream
@@ -149,7 +160,9 @@ class Structure:
         host_m = _pinned("m", (n, 4, 4), torch.float64) if self.with_mueller else None
         host_s = _pinned("s", (n, 4), torch.float64) if want_stokes else None
         host_p = _pinned("p", (planes, n), torch.float64) if planes else None
-        bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes)
+        host_t = _pinned("t", (4, n), torch.complex128) if self.with_transmission else None
+        bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
+                                     transmission=self.with_transmission)
                 for _ in range(2 if n > chunk else 1)]
         compute = torch.cuda.current_stream(prob.device)
         copy = torch.cuda.Stream(prob.device)
@@ -173,14 +186,18 @@ class Structure:
                     host_s[start:stop].copy_(buf.stokes[:m], non_blocking=True)
                 for i in range(planes):
                     host_p[i, start:stop].copy_(buf.power[i, :m], non_blocking=True)
+                if host_t is not None:
+                    for i in range(4):
+                        host_t[i, start:stop].copy_(buf.t[i, :m], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             done[ci % len(bufs)] = ev
         copy.synchronize()
-        self.d2h_bytes = n * (64 + (128 if host_m is not None else 0) + (32 if host_s is not None else 0) + 8 * planes)
-        self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, shape, to_numpy=True)
+        self.d2h_bytes = n * (64 + (128 if host_m is not None else 0) + (32 if host_s is not None else 0) + 8 * planes
+                              + (64 if host_t is not None else 0))
+        self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, host_t, shape, to_numpy=True)
 
-    def _assign(self, r, mueller, stokes, power, shape, to_numpy):
+    def _assign(self, r, mueller, stokes, power, trans, shape, to_numpy):
         if to_numpy:
             conv = (lambda t: np.array(t.numpy())) if self.own_results else (lambda t: t.numpy())
         else:
@@ -189,6 +206,11 @@ class Structure:
         self.r_pp, self.r_ps, self.r_sp, self.r_ss = (pres(conv(r[i])) for i in range(4))
         self.mueller = pres(conv(mueller.reshape(shape + (4, 4)))) if mueller is not None else None
         self.stokes = pres(conv(stokes.reshape(shape + (4,)))) if stokes is not None else None
+        if trans is not None:
+            t4 = trans.reshape((4,) + shape)
+            self.t_pp, self.t_ps, self.t_sp, self.t_ss = (pres(conv(t4[i])) for i in range(4))
+        else:
+            self.t_pp = self.t_ps = self.t_sp = self.t_ss = None
         self.power = None
         if power is not None:
             # planes per polarisation: R, T, A_0 .. A_{L-2}  (include/ho_b200.h, ho_outputs_t.power)

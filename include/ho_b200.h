@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 2
+#define HO_ABI_VERSION 3
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -105,6 +105,18 @@ typedef struct {
      i-th finite layer below the prism (i = 0 .. n_layers-2).  NULL to skip. */
   double* power;
   int64_t power_stride; /* >= n_end - n_begin */
+  /* Transmission amplitude coefficients, each [n_end - n_begin] complex128; all four or none.
+     Replaces Structure.calculate_transmissivity (structure.py:326-347: inverse of Gamma's forward
+     2x2 block) for the transfer backend and the t picks of scattering_coefficients
+     (scattering.py:155-164) for the scattering backend.  For a crystal exit they are amplitudes of
+     the reference's exit eigenmodes: numpy/LAPACK normalisation (unit 2-norm, largest component
+     real positive, waves.py:270) ordered by sort_poynting_indices (waves.py:474-510); when the
+     two forward modes are degenerate (isotropic crystal) that basis is not defined and the unit-E
+     basis of the forward plane is used. */
+  ho_c128* t_pp;
+  ho_c128* t_ps;
+  ho_c128* t_sp;
+  ho_c128* t_ss;
 } ho_outputs_t;
 
 /* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /

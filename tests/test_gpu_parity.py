@@ -326,7 +326,52 @@ def test_c4_full_size_properties(built_library):
     assert float(refl_p.max()) <= 1.0 + 1e-9 and float(refl_s.max()) <= 1.0 + 1e-9
     m00 = 0.5 * den
     assert float((s.mueller[:, 0, 0] - m00).abs().max()) <= 1e-12
-    # both layers are invariant under rotation about z (hBN c-axis along z, SiC isotropic): the
-    # result cannot depend on the azimuth
+    # both layers are invariant under rotation about z (hBN c-axis along z, SiC isotropic) up to
+    # the reference's hidden 1e-8 rad tilt (layers.py:283): the co-polarised coefficients cannot
+    # depend on the azimuth beyond second order in that tilt, the cross-polarised ones stay first
+    # order in it
     r = s.r.reshape(4, bench.F_PER_GPU, bench.N_INC, bench.N_AZ)
-    assert float((r - r[..., :1]).abs().max()) <= 1e-9
+    dev = (r - r[..., :1]).abs().amax(dim=(1, 2, 3))
+    assert float(dev[0]) <= 1e-9 and float(dev[3]) <= 1e-9
+    assert float(dev[1]) <= 1e-4 and float(dev[2]) <= 1e-4
+    assert float(r[1].abs().max()) <= 1e-4 and float(r[2].abs().max()) <= 1e-4
+
+
+T_KEYS = ("t_pp", "t_ps", "t_sp", "t_ss")
+# SiC is isotropic: its two forward modes are degenerate and the reference's t_* then depend on
+# which basis of the 2-d eigenspace LAPACK happens to return (not reproducible by construction)
+T_DEGENERATE_EXIT = ("c4_fullsweep_hbn_sic", "c5_thickness_11layer")
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if n not in T_DEGENERATE_EXIT])
+@pytest.mark.parametrize("backend", ["transfer", "scattering"])
+def test_transmission_coefficients(name, backend, built_library):
+    """t_pp, t_ps, t_sp, t_ss vs the reference (structure.py:326-347 / scattering.py:155-164): for a
+    crystal exit these are amplitudes of LAPACK-normalised, Poynting-ordered eigenmodes."""
+    fx = parity.load_fixture(name)
+    s = _run_gpu(name, backend, with_transmission=True)
+    prefix = "" if backend == "transfer" else "s_"
+    got = {k: parity.subsample(getattr(s, k), fx["strides"]) for k in T_KEYS}
+    with np.errstate(all="ignore"):
+        num = sum(np.abs(got[k] - fx[prefix + k]) ** 2 for k in T_KEYS)
+        den = sum(np.abs(fx[prefix + k]) ** 2 for k in T_KEYS)
+        err = np.sqrt(num / den)
+    # trust region: the reference's own two backends must agree on t (they do not at the grazing
+    # end points, where 1/cos(theta) = 1.6e16 turns t ~ 1e-16 into noise).  For a crystal exit the
+    # S-matrix picks are the transfer ones with the mode slots swapped.
+    crystal = ALL[name]["payload"]["Layers"][-1]["type"] == "Semi Infinite Anisotropic Layer"
+    pair = dict(t_pp="t_ps", t_ps="t_pp", t_sp="t_ss", t_ss="t_sp") if crystal else {k: k for k in T_KEYS}
+    with np.errstate(all="ignore"):
+        self_err = np.sqrt(sum(np.abs(fx[k] - fx["s_" + pair[k]]) ** 2 for k in T_KEYS) / den)
+    mask = parity.transfer_mask(fx) & np.isfinite(err) & (self_err <= 1e-9)
+    assert mask.mean() > 0.75
+    worst = float(np.nanmax(err[mask])) if np.ndim(err) else float(err)
+    # eigenvector-based quantities: conditioned by the gap between the two forward eigenvalues
+    # (Quartz at near-normal incidence), hence 1e-7 rather than the 1e-10 of r_*
+    assert worst <= 1e-7, f"{name}/{backend}: max t rel err {worst:.3e}"
+    # lazily, after a plain execute (the reference's calling pattern)
+    s2 = _run_gpu(name, backend)
+    assert s2.t_pp is None
+    s2.calculate_transmissivity()
+    np.testing.assert_array_equal(np.asarray(s2.t_pp), np.asarray(s.t_pp))
+    np.testing.assert_array_equal(np.asarray(s2.r_pp), np.asarray(s.r_pp))
