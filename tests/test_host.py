@@ -123,7 +123,10 @@ def test_library_exports_every_declared_symbol(built_library):
             "ho_last_error"} <= declared
     for sym in declared:
         assert hasattr(built_library, sym), f"{sym} declared in ho_b200.h but not exported"
-    assert built_library.ho_abi_version() == 1
+    from hyperbolic_optics_b200 import _native
+
+    version = int(re.search(r"#define HO_ABI_VERSION (\d+)", header).group(1))
+    assert built_library.ho_abi_version() == version == _native.HO_ABI_VERSION
     assert built_library.ho_launch_count() == 0
 
 
