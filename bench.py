@@ -268,6 +268,39 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---- end to end through the public API with host buffers ("e2e") ----
     # each rank runs its own 410-frequency slab as a stand-alone Structure.execute() call
     lo_f, hi_f = sharding.split_units(f_per * world, world, rank)
+    # ---- optional: the final gather over NVLink named in north_star (not part of the timed step) ----
+    gather = None
+    if world > 1 and not args.no_gather:
+        gathered = torch.empty((world, n_local), dtype=torch.complex128, device=device)
+        dist.all_gather_into_tensor(torch.view_as_real(gathered), torch.view_as_real(out.r[0].contiguous()))  # warm-up
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for i in range(4):
+            dist.all_gather_into_tensor(torch.view_as_real(gathered), torch.view_as_real(out.r[i].contiguous()))
+        g1.record(stream)
+        barrier()
+        g_ms = max_over_ranks(g0.elapsed_time(g1))
+        g_bytes = 4 * 16 * n_local * (world - 1)  # received per rank
+        same = bool(torch.equal(gathered[rank], out.r[3]))
+        gather = {"what": "NCCL all_gather of the four r_ij planes of every rank's slab (64 B/point)",
+                  "ms": g_ms, "received_bytes_per_rank": g_bytes, "GBps_per_rank": g_bytes / (g_ms * 1e-3) / 1e9,
+                  "ok": same}
+        del gathered
+    # host-memory guard: every rank pins its own result buffers (192 B/point)
+    e2e_f = hi_f - lo_f
+    e2e_reduced = False
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        need = world * e2e_f * n_inc * n_az * BYTES_PER_POINT * 1.15
+        if need > 0.6 * avail:
+            e2e_f = max(8, int(e2e_f * 0.6 * avail / need))
+            e2e_reduced = True
+    except ImportError:
+        pass
+    hi_f = lo_f + e2e_f
+    n_e2e = e2e_f * n_inc * n_az
     freqs = np.linspace(BAND[0], BAND[1], f_per * world)[lo_f:hi_f]
     e2e_payload = c4_payload(2)
     e2e_payload["ScenarioData"]["frequency"] = list(freqs)
@@ -285,7 +318,7 @@ def run_b200_arm(args, rank, local_rank, world):
         s.execute(e2e_payload, backend="transfer", own_results=False)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    e2e_value = n_local * world / e2e_s
+    e2e_value = n_e2e * world / e2e_s
     e2e_ok = bool(np.isfinite(s.r_pp[::37, ::41, ::43]).all() and s.r_pp.shape == (hi_f - lo_f, n_inc, n_az))
     h2d, d2h = s.h2d_bytes, s.d2h_bytes
 
@@ -323,7 +356,8 @@ def run_b200_arm(args, rank, local_rank, world):
             "sharding": "contiguous frequency slabs, one process per GPU, no data-path collective",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "path": "Structure.execute(payload) -> pinned host NumPy views", "ok": e2e_ok},
+                "steps": e2e_steps, "path": "Structure.execute(payload) -> pinned host NumPy views", "ok": e2e_ok,
+                "points_per_gpu": n_e2e, "reduced_grid_for_host_memory": e2e_reduced},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
@@ -345,6 +379,8 @@ def run_b200_arm(args, rank, local_rank, world):
         },
         "checks": {"finite": finite, "abs_sum_r": checksum},
     }
+    if gather is not None:
+        line["gather"] = gather
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         rate, pts, busy, wall, sample = cpu_port_throughput(2.5e4 * cores * 15.0, cores)
@@ -369,6 +405,7 @@ def main():
     ap.add_argument("--n-az", type=int, default=N_AZ)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the informational NVLink gather at N > 1")
     ap.add_argument("--cpu-seconds", type=float, default=150.0, help="total CPU-arm budget (reference arm)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
