@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--json", default="")
+    ap.add_argument("--dtype", default="c128", choices=["c128", "c64"], help="c64: the opt-in complex64 kernels")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     want = [s for s in args.only.split(",") if s]
@@ -67,8 +68,9 @@ def main():
         sc = ScenarioSetup(sd, n_incident=n_a, n_azimuthal=n_b)
         plan = build_plan(sc, layers)
         n = plan.n_points
-        planes = 2 * (len(plan.layers) + 1) if power else 0
-        out = engine.DeviceOutputs(n, dev, mueller=True, power_planes=planes)
+        planes = 2 * (len(plan.layers) + 1) if (power and args.dtype == "c128") else 0
+        out = engine.DeviceOutputs(n, dev, mueller=True, power_planes=planes,
+                                   dtype=torch.complex128 if args.dtype == "c128" else torch.complex64)
         for backend in backends:
             prob = engine.DeviceProblem(plan, backend, dev)
             for _ in range(3):
@@ -82,7 +84,7 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.reps
             finite = float(torch.isfinite(torch.view_as_real(out.r)).all(dim=(0, 2)).double().mean().item())
-            row = {"config": name, "backend": backend, "shape_FABT": list(plan.fabt_shape), "points": n,
+            row = {"config": name, "backend": backend, "dtype": args.dtype, "shape_FABT": list(plan.fabt_shape), "points": n,
                    "layers_below_prism": len(plan.layers), "power": power, "kernel_ms": ms,
                    "points_per_s": n / (ms * 1e-3), "finite_fraction": finite}
             rows.append(row)
