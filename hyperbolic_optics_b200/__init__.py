@@ -10,6 +10,7 @@ from .materials import create_material, list_materials
 from .mueller import Mueller
 from .scenario import ScenarioSetup
 from .structure import Structure
+from .sweep import ThicknessSweep
 
 __version__ = "0.1.0"
-__all__ = ["Structure", "ScenarioSetup", "Mueller", "FieldProfile", "create_material", "list_materials", "__version__"]
+__all__ = ["Structure", "ScenarioSetup", "Mueller", "FieldProfile", "ThicknessSweep", "create_material", "list_materials", "__version__"]

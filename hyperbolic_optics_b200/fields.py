@@ -36,6 +36,12 @@ class FieldProfile:
     def transmittance(self, polarization="p"):
         return self._block(polarization)["T"]
 
+    def transmission_coefficients(self):
+        """``t_ss, t_ps, t_sp, t_pp`` (reference ``fields.py:202-225``; equal to
+        ``Structure.calculate_transmissivity``)."""
+        self.structure.calculate_transmissivity()
+        return {k: getattr(self.structure, k) for k in ("t_ss", "t_ps", "t_sp", "t_pp")}
+
     def layer_absorption(self, polarization="p"):
         blk = self._block(polarization)
         return [{"index": i + 1, "type": self.layers[i + 1].type, "absorptance": a}

@@ -375,3 +375,41 @@ def test_transmission_coefficients(name, backend, built_library):
     s2.calculate_transmissivity()
     np.testing.assert_array_equal(np.asarray(s2.t_pp), np.asarray(s.t_pp))
     np.testing.assert_array_equal(np.asarray(s2.r_pp), np.asarray(s.r_pp))
+
+
+def test_thickness_sweep_helper_matches_reruns(built_library):
+    """ThicknessSweep (one launch over the T axis) == one Structure.execute per thickness, the
+    reference's own equivalence (tests/test_thickness_axis.py:63-81, atol 1e-10), with the
+    thickness axis in front like sweep.py."""
+    from hyperbolic_optics_b200 import FieldProfile, Structure, ThicknessSweep
+
+    payload = {"ScenarioData": {"type": "Incident", "frequency": list(np.linspace(1400.0, 1550.0, 5))},
+               "Layers": [{"type": "Ambient Incident Layer", "permittivity": 50.0},
+                          {"type": "Isotropic Middle-Stack Layer", "thickness": 0.2, "permittivity": 1.0},
+                          {"type": "Crystal Layer", "material": "Calcite", "thickness": 1.0, "rotationY": 60, "rotationZ": 10},
+                          {"type": "Semi Infinite Isotropic Layer", "permittivity": 2.0}]}
+    thick = [0.05, 0.4, 1.3]
+    for backend in ("transfer", "scattering"):
+        sweep = ThicknessSweep(payload, layer_index=2, thicknesses=thick, backend=backend, device="cuda:0")
+        assert len(sweep) == 3 and sweep.r_pp.shape == (3, 5, 360)
+        tc = sweep.transmission_coefficients()
+        la = sweep.layer_absorption("s")
+        assert [e["index"] for e in la] == [1, 2]
+        for i, d in enumerate(thick):
+            single = {"ScenarioData": payload["ScenarioData"], "Layers": [dict(x) for x in payload["Layers"]]}
+            single["Layers"][2]["thickness"] = d
+            s = Structure(device="cuda:0")
+            s.execute(single, backend=backend, power=True, transmission=True)
+            fp = FieldProfile(s)
+            mask = np.isfinite(s.r_pp) & np.isfinite(sweep.r_pp[i])
+            assert mask.mean() > 0.99
+            for k in parity.R_KEYS:
+                np.testing.assert_allclose(getattr(sweep, k)[i][mask], getattr(s, k)[mask], rtol=0, atol=1e-10)
+            for k in ("t_pp", "t_ss", "t_ps", "t_sp"):
+                np.testing.assert_allclose(tc[k][i][mask], getattr(s, k)[mask], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(sweep.reflectance("p")[i][mask], fp.reflectance("p")[mask], rtol=0, atol=1e-10)
+            np.testing.assert_allclose(sweep.transmittance("s")[i][mask], fp.transmittance("s")[mask], rtol=0, atol=1e-10)
+            np.testing.assert_allclose(la[1]["absorptance"][i][mask], fp.layer_absorption("s")[1]["absorptance"][mask],
+                                       rtol=0, atol=1e-10)
+            np.testing.assert_allclose(sweep.total_absorption("p")[i][mask], fp.summary("p")["total_absorption"][mask],
+                                       rtol=0, atol=1e-10)

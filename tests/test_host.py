@@ -157,3 +157,19 @@ def test_product_never_imports_oracle():
         text = path.read_text()
         assert "oracle" not in text.replace("# oracle", ""), f"{path} mentions the oracle"
         assert "tools." not in text and "from tools" not in text
+
+
+def test_thickness_sweep_argument_errors():
+    """Same guards as the reference helper (sweep.py:70-83); they fire before any device work."""
+    from hyperbolic_optics_b200 import ThicknessSweep
+
+    payload = {"ScenarioData": {"type": "Incident"},
+               "Layers": [{"type": "Ambient Incident Layer", "permittivity": 50.0},
+                          {"type": "Crystal Layer", "material": "Calcite", "thickness": 1.0, "rotationY": 90},
+                          {"type": "Semi Infinite Isotropic Layer", "permittivity": 1.0}]}
+    with pytest.raises(IndexError):
+        ThicknessSweep(payload, 7, [0.5])
+    with pytest.raises(ValueError):
+        ThicknessSweep(payload, 0, [0.5])
+    with pytest.raises(ValueError):
+        ThicknessSweep(payload, 1, [])
