@@ -383,7 +383,7 @@ template <typename T> __device__ __forceinline__ void rank1_clean(Vec4<T>& r0, V
   Vec4<T> v = sel(first, r0, r1), w = sel(first, r1, r0);
   T nv = first ? n0 : n1;
   cx<T> beta = mk<T>(T(0), T(0));
-  if (nv > T(0)) beta = (T(1) / nv) * dotc(v, w);
+  if (nv > T(0)) beta = ho_rcp(nv) * dotc(v, w);
   Vec4<T> wc = scale(beta, v);
   r0 = sel(first, v, wc);
   r1 = sel(first, wc, v);

@@ -48,7 +48,9 @@ template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p)
 // hundred cycles) out of L2 -- without this the spills cost ~180 B/point of DRAM write-back.
 __device__ __forceinline__ void st_stream(ho::cx<double>* p, ho::cx<double> v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
 __device__ __forceinline__ void st_stream(ho::cx<float>* p, ho::cx<float> v) { __stcs(reinterpret_cast<float2*>(p), make_float2(v.re, v.im)); }
-__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+// 8-byte plane stores (power, Stokes) stay plain: measured on the 22-plane thickness sweep, the
+// streaming hint costs 15 % there (8.2 -> 7.0 ms for 3.8e7 points)
+__device__ __forceinline__ void st_stream(double* p, double v) { *p = v; }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 
 template <typename T> __device__ __forceinline__ ho::Sym6<T> load_sym(const ho_c128* table, int row) {
@@ -202,13 +204,23 @@ __global__ void __launch_bounds__(kThreads, HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end) {
   using namespace ho;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = n_end <= (int64_t)0x7fffffff;
   for (int64_t n = n_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_end; n += stride) {
     // n = ((f*A + a)*B + b)*T + t   (presentation order, reference axes.py:83-95)
-    int64_t q = n;
-    const int t = (int)(q % P.T); q /= P.T;
-    const int b = (int)(q % P.B); q /= P.B;
-    const int a = (int)(q % P.A);
-    const int f = (int)(q / P.A);
+    int t, b, a, f;
+    if (small) {  // 32-bit index arithmetic when the grid allows it (64-bit div/mod is ~4x the work)
+      unsigned q = (unsigned)n;
+      t = (int)(q % (unsigned)P.T); q /= (unsigned)P.T;
+      b = (int)(q % (unsigned)P.B); q /= (unsigned)P.B;
+      a = (int)(q % (unsigned)P.A);
+      f = (int)(q / (unsigned)P.A);
+    } else {
+      int64_t q = n;
+      t = (int)(q % P.T); q /= P.T;
+      b = (int)(q % P.B); q /= P.B;
+      a = (int)(q % P.A);
+      f = (int)(q / P.A);
+    }
     const T k = T(__ldg(P.kx + a));
     const T k0 = T(__ldg(P.k0 + f));
 
@@ -254,6 +266,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
   const int64_t g_first = n_begin / P.T, g_last = (n_end - 1) / P.T;  // inclusive
   const int64_t n_units = (g_last - g_first + gpw) / gpw;
   const int n_lower = P.n_layers - 1 - swept;
+  const bool small = n_end <= (int64_t)0x7fffffff;
   for (int64_t unit = (int64_t)blockIdx.x * wpb + wib; unit < n_units; unit += (int64_t)gridDim.x * wpb) {
     const int64_t g0 = g_first + unit * gpw;
     const int ng = (int)min((int64_t)gpw, g_last + 1 - g0);
@@ -264,12 +277,24 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
       const int64_t n = p_lo + (int64_t)(pass - 1) * 32 + lane;
       const bool active = pass == 0 ? lane < ng : n < p_hi;
       if (active) {
-        int64_t q = pass == 0 ? g0 + lane : n / P.T;
-        const int t = pass == 0 ? 0 : (int)(n - q * P.T);
+        int64_t q;
+        int t, b, a, f;
+        if (small) {  // 32-bit index arithmetic when the grid allows it
+          unsigned qq = pass == 0 ? (unsigned)(g0 + lane) : (unsigned)n / (unsigned)P.T;
+          t = pass == 0 ? 0 : (int)((unsigned)n - qq * (unsigned)P.T);
+          q = qq;
+          b = (int)(qq % (unsigned)P.B); qq /= (unsigned)P.B;
+          a = (int)(qq % (unsigned)P.A);
+          f = (int)(qq / (unsigned)P.A);
+        } else {
+          q = pass == 0 ? g0 + lane : n / P.T;
+          t = pass == 0 ? 0 : (int)(n - q * P.T);
+          int64_t qq = q;
+          b = (int)(qq % P.B); qq /= P.B;
+          a = (int)(qq % P.A);
+          f = (int)(qq / P.A);
+        }
         double* mine = park + (size_t)(q - g0) * row;
-        const int b = (int)(q % P.B); q /= P.B;
-        const int a = (int)(q % P.A);
-        const int f = (int)(q / P.A);
         const T k = __ldg(P.kx + a), k0 = __ldg(P.k0 + f);
         Vec4<T> y0, y1;
         T hf[POWER ? HO_MAX_LAYERS : 1][4];
@@ -319,9 +344,11 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
             }
             // exit-mode map folded with the lower maps: coordinates at the top of layer swept+1
             // -> reference exit-mode amplitudes
-            cx<T>* pb = reinterpret_cast<cx<T>*>(mine + 16 + 4 * n_lower);
-            pb[0] = fma(binv[1], m10, binv[0] * m00); pb[1] = fma(binv[1], m11, binv[0] * m01);
-            pb[2] = fma(binv[3], m10, binv[2] * m00); pb[3] = fma(binv[3], m11, binv[2] * m01);
+            if (out.t_pp) {  // the row only has these 8 doubles when transmission outputs are requested
+              cx<T>* pb = reinterpret_cast<cx<T>*>(mine + 16 + 4 * n_lower);
+              pb[0] = fma(binv[1], m10, binv[0] * m00); pb[1] = fma(binv[1], m11, binv[0] * m01);
+              pb[2] = fma(binv[3], m10, binv[2] * m00); pb[3] = fma(binv[3], m11, binv[2] * m01);
+            }
           }
         } else {
           emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, swept + 1, mine + 16,
@@ -412,7 +439,7 @@ int launch_tsweep(const ho_problem_t* p, const OutPtrs<double>& out, int64_t n_b
     int v = atoi(env);
     if (v >= 1 && v <= 32) gpw = v;
   }
-  int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) + 8 : 0);
+  int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) + (out.t_pp ? 8 : 0) : 0);
   row |= 1;  // odd row length: lane <-> row accesses in pass 0 are bank-conflict free
   const int wpb = kSweepThreads / 32;
   const size_t smem = (size_t)wpb * gpw * row * sizeof(double);

@@ -32,8 +32,38 @@ template <typename T> __device__ __forceinline__ cx<T> cmulc(cx<T> a, cx<T> b) {
   return mk<T>(a.re * b.re + a.im * b.im, a.re * b.im - a.im * b.re);
 }
 template <typename T> __device__ __forceinline__ cx<T> mul_i(cx<T> a) { return mk<T>(-a.im, a.re); }  // i*a
+// Branch-free FP64 reciprocal and (sqrt, rsqrt): MUFU seed (rcp/rsqrt.approx.ftz.f64, ~2^-20) plus
+// two Newton rounds on the FP64 pipe.  The library versions (1.0/x, sqrt, rsqrt) are IEEE-exact but
+// carry a slow-path call that splits every use into separate basic blocks; these serial chains
+// (~5 dependent DFMAs each, ~30 per point) are where a 4-warp scheduler starves, and without the
+// branches the compiler interleaves neighbouring ones.  Accuracy ~1 ulp (parity bar is 1e-10).
+// Special values: 0 and inf give NaN instead of inf/0 -- callers that can see an exact zero
+// select around it; inf only occurs after a transfer-backend overflow, whose results are
+// non-finite by contract.  Denormal inputs flush to zero.
+__device__ __forceinline__ double ho_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = ::fma(-x, y, 1.0);
+  y = ::fma(y, e, y);
+  e = ::fma(-x, y, 1.0);
+  return ::fma(y, e, y);
+}
+__device__ __forceinline__ float ho_rcp(float x) { return 1.f / x; }
+// s = sqrt(x), rs = 1/sqrt(x) by the coupled (Goldschmidt) iteration
+__device__ __forceinline__ void ho_sqrt_rsqrt(double x, double& s, double& rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = ::fma(-h, g, 0.5);
+  g = ::fma(g, r, g); h = ::fma(h, r, h);
+  r = ::fma(-h, g, 0.5);
+  g = ::fma(g, r, g); h = ::fma(h, r, h);
+  s = g; rs = h + h;
+}
+__device__ __forceinline__ void ho_sqrt_rsqrt(float x, float& s, float& rs) { rs = rsqrtf(x); s = x * rs; }
+
 __device__ __forceinline__ cx<double> recip(cx<double> a) {
-  double inv = 1.0 / norm2(a);
+  double inv = ho_rcp(norm2(a));
   return mk<double>(a.re * inv, -a.im * inv);
 }
 // FP32: |a|^2 overflows already at |a| ~ 1.8e19 (the prism's 1/cos(theta) reaches 1.6e16 at the
@@ -68,17 +98,17 @@ __device__ __forceinline__ float ho_copysign(float x, float y) { return copysign
 
 template <typename T> __device__ __forceinline__ T cabs(cx<T> a) { return ho_sqrt(norm2(a)); }
 
-// principal square root.  Two reciprocal square roots instead of two square roots and a
-// division: t = sqrt(x) = x rsqrt(x) and 1/t = rsqrt(x) come from the same MUFU seed.
+// principal square root, branch-free: sqrt|z| and then (t, 1/t) of t^2 = (|z| + |re|)/2 from one
+// coupled iteration each -- no division, no second square root.
 template <typename T> __device__ __forceinline__ cx<T> csqrt(cx<T> z) {
   T n2 = norm2(z);
-  if (n2 == T(0)) return mk<T>(T(0), T(0));
-  T r = n2 * ho_rsqrt(n2);
+  T r, unused, t, it;
+  ho_sqrt_rsqrt(n2, r, unused);
   T x = T(0.5) * (r + ho_abs(z.re));
-  T it = ho_rsqrt(x);
-  T t = x * it;
+  ho_sqrt_rsqrt(x, t, it);
   T u = (T(0.5) * z.im) * it;
-  return (z.re >= T(0)) ? mk<T>(t, u) : mk<T>(ho_abs(u), ho_copysign(t, z.im));
+  cx<T> w = (z.re >= T(0)) ? mk<T>(t, u) : mk<T>(ho_abs(u), ho_copysign(t, z.im));
+  return (n2 > T(0)) ? w : mk<T>(T(0), T(0));
 }
 
 // principal cube root
