@@ -25,8 +25,12 @@ int fail(int code, const char* fmt, const char* detail = "") {
   return code;
 }
 
+// Launch shape of the point-per-thread kernel: 3 CTAs of 128 threads per SM = 168 registers per
+// thread, 12 warps per SM.  Measured on C1-C5 against 256x2 (128 registers, 16 warps, 544 B of
+// spills per thread) and 256x1 (236 registers, 8 warps, no spills): best or within 2 % of the
+// best on every configuration (profiles/README.md).
 #ifndef HO_THREADS
-#define HO_THREADS 256
+#define HO_THREADS 128
 #endif
 constexpr int kThreads = HO_THREADS;
 
@@ -76,7 +80,7 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 }
 
 #ifndef HO_MIN_BLOCKS
-#define HO_MIN_BLOCKS 2
+#define HO_MIN_BLOCKS 3
 #endif
 
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
