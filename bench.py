@@ -190,6 +190,24 @@ def run_reference_arm(args, rank, world):
     return 0
 
 
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this rank on the CPUs NVML reports as local to its GPU, so that the pinned
+    result buffers (first touch) and the D2H traffic stay on the GPU's NUMA node."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001 - NVML missing / containerised CPU sets: keep the default placement
+        return 0
+
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200_arm(args, rank, local_rank, world):
     import torch
@@ -204,6 +222,8 @@ def run_b200_arm(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the reflection engine has no CPU fallback")
+    if world > 1:
+        bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:

@@ -413,3 +413,73 @@ def test_thickness_sweep_helper_matches_reruns(built_library):
                                        rtol=0, atol=1e-10)
             np.testing.assert_allclose(sweep.total_absorption("p")[i][mask], fp.summary("p")["total_absorption"][mask],
                                        rtol=0, atol=1e-10)
+
+
+def _config_bench_plan(name):
+    from hyperbolic_optics_b200.plan import build_plan
+    from hyperbolic_optics_b200.scenario import ScenarioSetup
+    from tools.config_bench import configs
+
+    sd, layers, n_a, n_b, _, _ = configs()[name]
+    return build_plan(ScenarioSetup(sd, n_incident=n_a, n_azimuthal=n_b), layers)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_c2_c3_full_size_properties(name, built_library):
+    """BASELINE configs 2 (Dispersion 1024 x 1024, MoO3) and 3 (Azimuthal 2000 x 720, Quartz) at
+    full size: the two independent recursions agree to 1e-10 everywhere, passivity, M00 identity."""
+    from hyperbolic_optics_b200 import engine
+
+    plan = _config_bench_plan(name)
+    assert plan.n_points in (1024 * 1024, 2000 * 720)
+    res = {}
+    for backend in ("transfer", "scattering"):
+        prob = engine.DeviceProblem(plan, backend, "cuda:0")
+        out = engine.DeviceOutputs(plan.n_points, prob.device)
+        engine.reflect(prob, out)
+        res[backend] = out
+    torch.cuda.synchronize()
+    t, s = res["transfer"], res["scattering"]
+    assert bool(torch.isfinite(torch.view_as_real(s.r)).all())
+    den = s.r.abs().square().sum(dim=0)
+    err = ((t.r - s.r).abs().square().sum(dim=0) / den).sqrt()
+    fin = torch.isfinite(err)
+    assert float(fin.double().mean()) > 0.999          # transfer may overflow at the grazing end points
+    assert float(err[fin].max()) <= 1e-10
+    assert float((s.r[0].abs().square() + s.r[1].abs().square()).max()) <= 1.0 + 1e-9
+    assert float((s.mueller[:, 0, 0] - 0.5 * den).abs().max()) <= 1e-12
+
+
+def test_c5_full_size_properties(built_library):
+    """BASELINE config 5 at full size (11-layer lossy stack, 64 x 90 x 80 thickness sweep,
+    scattering backend, layer-resolved absorption): R from fluxes equals |r_co|^2 + |r_cross|^2,
+    R + T + sum A_i = 1, every layer is passive, everything finite -- and the thickness-sweep
+    kernel reproduces the point-per-thread kernel on the same grid."""
+    import os
+
+    from hyperbolic_optics_b200 import engine
+
+    plan = _config_bench_plan("c5")
+    n = plan.n_points
+    assert plan.fabt_shape == (64, 90, 1, 80) and len(plan.layers) == 10
+    planes = 2 * (len(plan.layers) + 1)
+    prob = engine.DeviceProblem(plan, "scattering", "cuda:0")
+    out = engine.DeviceOutputs(n, prob.device, power_planes=planes)
+    engine.reflect(prob, out)
+    os.environ["HO_B200_TSWEEP"] = "0"
+    try:
+        ref = engine.DeviceOutputs(n, prob.device, power_planes=planes)
+        engine.reflect(prob, ref)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["HO_B200_TSWEEP"]
+    assert bool(torch.isfinite(out.power).all()) and bool(torch.isfinite(torch.view_as_real(out.r)).all())
+    assert float((out.power - ref.power).abs().max()) <= 1e-11
+    assert float((out.r - ref.r).abs().max()) <= 1e-11
+    per = planes // 2
+    for pol, (co, cross) in enumerate(((0, 1), (3, 2))):   # p: r_pp, r_ps ; s: r_ss, r_sp
+        blk = out.power[pol * per:(pol + 1) * per]
+        r_amp = out.r[co].abs().square() + out.r[cross].abs().square()
+        assert float((blk[0] - r_amp).abs().max()) <= 1e-9
+        assert float((blk.sum(dim=0) - 1.0).abs().max()) <= 1e-12
+        assert float(blk[1:].min()) >= -1e-9
