@@ -360,13 +360,16 @@ template <typename T, bool NM> __device__ __forceinline__ Vec4<T> project_forwar
 }
 
 // Root pair (sum s, product p) ordered by |exp(c lambda)|: exp(c K) = phi_s I + dd (K - lam_s I)
-template <typename T> __device__ __forceinline__ void pair_modes(cx<T> s, cx<T> p, cx<T> c, cx<T>& lam_s, cx<T>& phi_s, cx<T>& dd, bool& separated) {
+// growth = max |Re(c lambda)| of the two modes
+template <typename T> __device__ __forceinline__ void pair_modes(cx<T> s, cx<T> p, cx<T> c, cx<T>& lam_s, cx<T>& phi_s, cx<T>& dd, bool& separated, T& growth) {
   cx<T> m = T(0.5) * s;
   cx<T> h = csqrt(m * m - p);
   if ((c * h).re < T(0)) h = -h;
   lam_s = m - h;
   cx<T> lam_g = m + h;
-  phi_s = cexp(c * lam_s);
+  cx<T> cs = c * lam_s;
+  growth = fmax(ho_abs(cs.re), ho_abs((c * lam_g).re));
+  phi_s = cexp(cs);
   cx<T> x = T(2) * (c * h);
   separated = x.re > T(1);
   if (norm2(x) < T(0.25)) {
@@ -389,29 +392,64 @@ template <typename T> __device__ __forceinline__ void rank1_clean(Vec4<T>& r0, V
   r1 = sel(first, wc, v);
 }
 
-// exp(c D) applied to two columns lying in one invariant subspace (root pair s, p)
-template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> s, cx<T> p, cx<T> c, const Vec4<T>& z0, const Vec4<T>& z1,
+// exp(c D) applied to two columns lying in one invariant subspace, given the pair's modes
+template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> lam_s, cx<T> phi_s, cx<T> dd, bool separated,
+                                                                     const Vec4<T>& z0, const Vec4<T>& z1,
                                                                      const Vec4<T>& dz0, const Vec4<T>& dz1, Vec4<T>& o0, Vec4<T>& o1) {
-  cx<T> lam_s, phi_s, dd;
-  bool separated;
-  pair_modes(s, p, c, lam_s, phi_s, dd, separated);
   Vec4<T> r0 = axpy(-lam_s, z0, dz0), r1 = axpy(-lam_s, z1, dz1);
   if (separated) rank1_clean(r0, r1);
   o0 = axpy(dd, r0, scale(phi_s, z0));
   o1 = axpy(dd, r1, scale(phi_s, z1));
 }
 
-// exp(c D) Y, unnormalised (transfer-matrix semantics: overflows for thick evanescent layers)
+// y <- (a0 + a1 D + a2 D^2 + a3 D^3) y: three mat-vecs, one accumulator
+template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const Delta<T, NM>& D, cx<T> a0, cx<T> a1, cx<T> a2, cx<T> a3, Vec4<T>& y) {
+  Vec4<T> v = matvec(D, y);
+  Vec4<T> o = axpy(a1, v, scale(a0, y));
+  v = matvec(D, v);
+  o = axpy(a2, v, o);
+  v = matvec(D, v);
+  y = axpy(a3, v, o);
+}
+
+// exp(c D) Y, unnormalised (transfer-matrix semantics: overflows for thick evanescent layers).
+// Thin films (all four |Re(c lambda)| < 3, i.e. mode exponentials within e^6 of each other) take
+// the exponential as ONE cubic polynomial in D,
+//   E(x) = alpha_b(x) + (alpha_f(x) - alpha_b(x)) q_b(x) h(x)   mod   q_f(x) q_b(x),
+// alpha_{f,b} the linear interpolants of exp(c x) on each root pair: 6 mat-vecs instead of 8 and
+// no projected intermediates.  Mixing all four exponentials in one polynomial costs log10 of their
+// ratio in digits (<= 2.6 here); thick films -- where that form loses the sub-dominant growing
+// mode, SURVEY 7.0-6a -- keep the invariant-subspace block form.
 template <typename T, bool NM> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
+  cx<T> lf, phf, ddf, lb, phb, ddb;
+  bool sepf, sepb;
+  T gf, gb;
+  pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
+  pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
+  if (gf < T(3) && gb < T(3)) {
+    // alpha(x) = (phi_s - dd lam_s) + dd x on each pair
+    cx<T> ab0 = phb - ddb * lb;
+    cx<T> d0 = (phf - ddf * lf) - ab0, d1 = ddf - ddb;
+    cx<T> g0 = d0 * h0, g1 = fma(d1, h0, d0 * h1), g2 = d1 * h1;
+    // q_f q_b = x^4 + c3 x^3 + c2 x^2 + c1 x + c0
+    cx<T> c3 = -(s.sf + s.sb), c2 = fma(s.sf, s.sb, s.pf + s.pb), c1 = -fma(s.sf, s.pb, s.sb * s.pf), c0 = s.pf * s.pb;
+    cx<T> a3 = g1 - g2 * (s.sb + c3);
+    cx<T> a2 = fma(g2, s.pb - c2, g0 - s.sb * g1);
+    cx<T> a1 = fma(s.pb, g1, ddb - s.sb * g0) - g2 * c1;
+    cx<T> a0 = fma(s.pb, g0, ab0) - g2 * c0;
+    cubic_apply(D, a0, a1, a2, a3, y0);
+    cubic_apply(D, a0, a1, a2, a3, y1);
+    return;
+  }
   Vec4<T> dy0, dy1;
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy0);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy1);
   Vec4<T> dzf0 = matvec(D, zf0), dzf1 = matvec(D, zf1);
   Vec4<T> f0, f1, b0, b1;
-  block_exp_apply(s.sf, s.pf, c, zf0, zf1, dzf0, dzf1, f0, f1);
-  block_exp_apply(s.sb, s.pb, c, sub(y0, zf0), sub(y1, zf1), sub(dy0, dzf0), sub(dy1, dzf1), b0, b1);
+  block_exp_apply(lf, phf, ddf, sepf, zf0, zf1, dzf0, dzf1, f0, f1);
+  block_exp_apply(lb, phb, ddb, sepb, sub(y0, zf0), sub(y1, zf1), sub(dy0, dzf0), sub(dy1, dzf1), b0, b1);
   y0 = add(f0, b0);
   y1 = add(f1, b1);
 }
@@ -445,11 +483,12 @@ template <typename T, bool NM> __device__ __forceinline__ void film_stable(const
   cx<T> lam, phi, dd;
   bool sep;
   // g = L exp(-c K_f) X_f  (2x2): forward modes run back down the film, decaying
-  pair_modes(s.sf, s.pf, -c, lam, phi, dd, sep);
+  T growth;
+  pair_modes(s.sf, s.pf, -c, lam, phi, dd, sep, growth);
   Vec4<T> g0 = lin_apply(phi, dd, lam, xf0, matvec(D, xf0));
   Vec4<T> g1 = lin_apply(phi, dd, lam, xf1, matvec(D, xf1));
   // exp(+c K_b) X_b: backward modes up the film, decaying
-  pair_modes(s.sb, s.pb, c, lam, phi, dd, sep);
+  pair_modes(s.sb, s.pb, c, lam, phi, dd, sep, growth);
   Vec4<T> e0 = lin_apply(phi, dd, lam, xb0, matvec(D, xb0));
   Vec4<T> e1 = lin_apply(phi, dd, lam, xb1, matvec(D, xb1));
   y0 = axpy(g0.v1, e1, axpy(g0.v0, e0, xf0));

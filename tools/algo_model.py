@@ -408,8 +408,11 @@ def block_exp_apply(D, Z, s, p, cfac, clean=True):
     return [tuple(phi_s * Z[k][i] + dd * R[k][i] for i in range(4)) for k in range(2)]
 
 
-def film_transfer(D, Y, spec, cfac, clean=True):
-    """exp(cfac D) applied to both columns of Y (list of two 4-tuples). Unnormalised."""
+MONO_GROWTH = 3.0  # thin-film switch: all four |Re(cfac lambda)| below this -> one cubic polynomial
+
+
+def film_transfer(D, Y, spec, cfac, clean=True, mono=True):
+    """exp(cfac D) Y: invariant-subspace block form, or (thin films) the monolithic cubic."""
     sf, pf, sb, pb = spec
     zf, zb = [], []
     for y in Y:
@@ -418,7 +421,12 @@ def film_transfer(D, Y, spec, cfac, clean=True):
         zb.append(tuple(y[i] - z[i] for i in range(4)))
     gf = block_exp_apply(D, zf, sf, pf, cfac, clean)
     gb = block_exp_apply(D, zb, sb, pb, cfac, clean)
-    return [tuple(gf[k][i] + gb[k][i] for i in range(4)) for k in range(2)]
+    block = [tuple(gf[k][i] + gb[k][i] for i in range(4)) for k in range(2)]
+    if not mono:
+        return block
+    thin = film_growth(spec, cfac) < MONO_GROWTH
+    poly = film_transfer_mono(D, Y, spec, cfac)
+    return [tuple(np.where(thin, poly[k][i], block[k][i]) for i in range(4)) for k in range(2)]
 
 
 def _inv2(m00, m01, m10, m11):
@@ -601,3 +609,41 @@ def incident_coords(Y, inv_c, inv_nc, inv_n, a_s, a_p):
     (g00, g20), (g02, g22) = g
     idet = 1.0 / (g00 * g22 - g02 * g20)
     return (g22 * a_s - g02 * a_p) * idet, (g00 * a_p - g20 * a_s) * idet
+
+
+# ----------------------------------------------------------------------------- thin films: monolithic cubic
+def film_transfer_mono(D, Y, spec, cfac):
+    """exp(cfac D) Y as ONE cubic polynomial in D (3 mat-vecs per column):
+    E(x) = alpha_b(x) + (alpha_f(x) - alpha_b(x)) q_b(x) h(x)  mod  q_f(x) q_b(x).
+    Only safe when the exponentials of the four modes are of comparable size (thin films)."""
+    sf, pf, sb, pb = spec
+    Af, Bf, mf = pair_exponential(sf, pf, cfac)
+    Ab, Bb, mb = pair_exponential(sb, pb, cfac)
+    af0, af1 = Af - Bf * mf, Bf
+    ab0, ab1 = Ab - Bb * mb, Bb
+    h0, h1 = projector_coeffs(sf, pf, sb, pb)
+    d0, d1 = af0 - ab0, af1 - ab1
+    g0, g1, g2 = d0 * h0, d0 * h1 + d1 * h0, d1 * h1
+    c3, c2, c1, c0 = -(sf + sb), pf + pb + sf * sb, -(sf * pb + sb * pf), pf * pb
+    a3 = g1 - sb * g2 - g2 * c3
+    a2 = g0 - sb * g1 + pb * g2 - g2 * c2
+    a1 = -sb * g0 + pb * g1 - g2 * c1 + ab1
+    a0 = pb * g0 - g2 * c0 + ab0
+    out = []
+    for y in Y:
+        v1 = matvec(D, y)
+        v2 = matvec(D, v1)
+        v3 = matvec(D, v2)
+        out.append(tuple(a0 * y[i] + a1 * v1[i] + a2 * v2[i] + a3 * v3[i] for i in range(4)))
+    return out
+
+
+def film_growth(spec, cfac):
+    """max |Re(cfac lambda)| over the four modes."""
+    sf, pf, sb, pb = spec
+    g = 0.0
+    for s, p in ((sf, pf), (sb, pb)):
+        m = 0.5 * s
+        h = np.sqrt(m * m - p)
+        g = np.maximum(g, np.maximum(np.abs((cfac * (m + h)).real), np.abs((cfac * (m - h)).real)))
+    return g
