@@ -229,27 +229,30 @@ template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4
   bool cplx[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { cplx[i] = ho_abs(lam[i].im) > tol; n_c += cplx[i] ? 1 : 0; }
-  T k1[4], k2[4];
+  int k1[4];
+  T k2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    T score = cplx[i] ? (lam[i].im > T(0) ? T(2) : T(-2)) : (lam[i].re > T(0) ? T(1) : T(-1));
-    k1[i] = (n_c == 4 || n_c == 0) ? T(0) : score;
+    int score = cplx[i] ? (lam[i].im > T(0) ? 2 : -2) : (lam[i].re > T(0) ? 1 : -1);
+    k1[i] = (n_c == 4 || n_c == 0) ? 0 : score;
     k2[i] = (n_c == 0) ? lam[i].re : lam[i].im;
   }
+  // rank = number of roots that sort before this one (lexicographic k1, k2, Re; index breaks
+  // ties, so the order is strict and each unordered pair needs one evaluation)
+  int rank[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int rank = 0;
 #pragma unroll
-    for (int jx = 0; jx < 4; ++jx) {
-      if (jx == i) continue;
-      bool better = (k1[jx] > k1[i]) ||
-                    (k1[jx] == k1[i] && ((k2[jx] > k2[i]) ||
-                                         (k2[jx] == k2[i] && ((lam[jx].re > lam[i].re) ||
-                                                              (lam[jx].re == lam[i].re && jx < i)))));
-      rank += better ? 1 : 0;
+    for (int jx = i + 1; jx < 4; ++jx) {
+      // does jx sort before i?  (on a full tie the lower index i wins)
+      bool j_first = (k1[jx] > k1[i]) ||
+                     (k1[jx] == k1[i] && ((k2[jx] > k2[i]) || (k2[jx] == k2[i] && lam[jx].re > lam[i].re)));
+      rank[i] += j_first ? 1 : 0;
+      rank[jx] += j_first ? 0 : 1;
     }
-    fwd[i] = rank < 2;
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) fwd[i] = rank[i] < 2;
 }
 
 // Bairstow: Newton on (u, v) so that lambda^2 + u lambda + v divides the quartic; the

@@ -111,14 +111,40 @@ template <typename T> __device__ __forceinline__ cx<T> csqrt(cx<T> z) {
   return (n2 > T(0)) ? w : mk<T>(T(0), T(0));
 }
 
-// principal cube root
-template <typename T> __device__ __forceinline__ cx<T> ccbrt(cx<T> z) {
-  T r = cabs(z);
-  T th = ho_atan2(z.im, z.re) * T(1.0 / 3.0);
-  T s, c;
-  ho_sincos(th, &s, &c);
-  T cr = ho_cbrt(r);
-  return mk<T>(cr * c, cr * s);
+// principal cube root (float: library polar form)
+__device__ __forceinline__ cx<float> ccbrt(cx<float> z) {
+  float r = cabs(z);
+  float th = atan2f(z.im, z.re) * (1.0f / 3.0f);
+  float s, c;
+  sincosf(th, &s, &c);
+  float cr = cbrtf(r);
+  return mk<float>(cr * c, cr * s);
+}
+// principal cube root (double): polar form evaluated in FP32 on the power-of-8 scaled argument
+// (FP32/MUFU pipes, off the FP64 critical path), then two Newton rounds u <- (2u + z/u^2)/3 in
+// FP64 (2e-7 -> 1e-13 -> rounding).  Branch-free; replaces atan2 + sincos + cbrt of the FP64
+// library (115 FP64 instructions and three slow-path calls).  The Newton rounds stay on the
+// principal branch because the seed is within 1e-6 of it.
+__device__ __forceinline__ cx<double> ccbrt(cx<double> z) {
+  const double big = fmax(fabs(z.re), fabs(z.im));
+  // exponent of the larger component, rounded down to a multiple of 3
+  const int ex = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+  const int e3 = (ex >= 0 ? ex : ex - 2) / 3;
+  const double down = __hiloint2double((1023 - 3 * e3) << 20, 0);  // 2^(-3 e3)
+  const double up = __hiloint2double((1023 + e3) << 20, 0);        // 2^(e3)
+  const float fr = (float)(z.re * down), fi = (float)(z.im * down);  // |.| in [1, 8)
+  const float r = sqrtf(fr * fr + fi * fi);
+  const float th = atan2f(fi, fr) * (1.0f / 3.0f);
+  float sn, cs;
+  __sincosf(th, &sn, &cs);
+  const float cr = cbrtf(r);
+  cx<double> u = mk<double>((double)(cr * cs) * up, (double)(cr * sn) * up);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    cx<double> t = z * recip(u * u);
+    u = mk<double>((2.0 * u.re + t.re) * (1.0 / 3.0), (2.0 * u.im + t.im) * (1.0 / 3.0));
+  }
+  return (big > 0.0) ? u : mk<double>(0.0, 0.0);
 }
 
 template <typename T> __device__ __forceinline__ cx<T> cexp(cx<T> z) {
