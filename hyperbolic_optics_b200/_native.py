@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 3
+HO_ABI_VERSION = 4
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -24,7 +24,7 @@ class c128(C.Structure):
 class LayerDesc(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("n_eps", C.c_int32), ("n_mu", C.c_int32), ("mu_scalar", C.c_int32),
-        ("n_beta", C.c_int32), ("n_thickness", C.c_int32),
+        ("n_beta", C.c_int32), ("n_thickness", C.c_int32), ("eps_scalar", C.c_int32),
         ("eps", C.c_void_p), ("mu", C.c_void_p),
         ("cos_beta", C.c_void_p), ("sin_beta", C.c_void_p), ("thickness", C.c_void_p),
         ("iso_eps", c128), ("iso_mu", c128),

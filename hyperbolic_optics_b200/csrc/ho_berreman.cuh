@@ -562,6 +562,18 @@ template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, c
   w[0] = n00 * ph; w[1] = n01 * ph; w[2] = n10 * ph; w[3] = n11 * ph;
 }
 
+// Forward plane of a semi-infinite ISOTROPIC crystal (scalar complex eps(f), mu(f)): the modes of
+// SURVEY A.13, s = (0, -mu, kz, 0) and p = (mu - k^2/eps, 0, 0, kz), kz the forward root of
+// eps mu - k^2 by the reference's rule (waves.py:273-289).  Same plane as the general path's
+// q_b(D) [e0 e1] for that medium (double forward root), without the quartic.
+template <typename T> __device__ __forceinline__ void iso_crystal_exit_plane(T k, cx<T> eps, cx<T> mu, Vec4<T>& y0, Vec4<T>& y1) {
+  const cx<T> zero = mk<T>(T(0), T(0));
+  T k2 = k * k;
+  cx<T> kz = forward_sqrt(eps * mu - k2);
+  y0.v0 = zero; y0.v1 = -mu; y0.v2 = kz; y0.v3 = zero;
+  y1.v0 = mu - k2 * recip(eps); y1.v1 = zero; y1.v2 = zero; y1.v3 = kz;
+}
+
 // columns 0 and 2 of the isotropic exit matrix (reference layers.py:190-238)
 template <typename T> __device__ __forceinline__ void exit_iso_plane(cx<T> cf, T n_exit, Vec4<T>& y0, Vec4<T>& y1) {
   const cx<T> one = mk<T>(T(1), T(0)), zero = mk<T>(T(0), T(0));

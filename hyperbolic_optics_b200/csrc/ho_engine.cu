@@ -97,6 +97,18 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
     const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
     iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
+  } else if (L.eps_scalar && L.mu_scalar) {
+    // isotropic crystal (scalar eps(f), mu(f), e.g. SiC): closed-form modes, no quartic
+    const cx<T> eps = ldc<T>(L.eps + 6 * (int64_t)(L.n_eps > 1 ? f : 0));
+    const cx<T> mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
+    if (L.kind == HO_ANISO_EXIT) {
+      iso_crystal_exit_plane(k, eps, mu, y0, y1);
+      // transmission amplitudes of a degenerate exit: (Ex, Ey) of the transmitted field, as in exit_mode_basis
+      if constexpr (EXTRAS) { binv[0] = y0.v0; binv[1] = y1.v0; binv[2] = y0.v1; binv[3] = y1.v1; }
+    } else {
+      const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
+      iso_film(k, eps, mu, mk<T>(T(0), -(k0 * d)), STABLE, y0, y1, w);
+    }
   } else {
     // crystal film or crystal exit: one instance of the Delta assembly + spectral split
     ZRow<T> z;

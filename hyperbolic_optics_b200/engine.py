@@ -51,6 +51,7 @@ class DeviceProblem:
             L = d.layers[i]
             L.kind = lp.kind
             L.mu_scalar = 1 if lp.mu_scalar else 0
+            L.eps_scalar = 1 if lp.eps_scalar else 0
             L.iso_eps = nat.c128(lp.iso_eps.real, lp.iso_eps.imag)
             L.iso_mu = nat.c128(lp.iso_mu.real, lp.iso_mu.imag)
             L.exit_n = lp.exit_n

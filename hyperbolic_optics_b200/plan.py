@@ -47,6 +47,7 @@ class LayerPlan:
     eps: np.ndarray | None = None      # [Fe, 6] complex128, Fe in {1, F}
     mu: np.ndarray | None = None       # [Fm, 6] complex128, Fm in {1, F}
     mu_scalar: bool = True             # mu proportional to identity (rotation-invariant)
+    eps_scalar: bool = False           # eps proportional to identity at every frequency (isotropic crystal)
     cos_beta: np.ndarray | None = None  # [Bb] float64, Bb in {1, B}
     sin_beta: np.ndarray | None = None
     thickness: np.ndarray | None = None  # [Tt] float64 cm, Tt in {1, T}
@@ -196,7 +197,12 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
             rot_z = np.float64(math.radians(data.get("rotationZ", 0))) + 1.0e-9
             mode = data.get("rotationZType", "relative")
             q = _rotation_xy(theta_x, theta_y)
-            eps = pack_symmetric(q @ unpack_symmetric(material.eps_packed(frequency)) @ q.T)
+            eps_packed = material.eps_packed(frequency)
+            # isotropic crystal (SiC): R (eps I) R^T = eps I, keep the table exact instead of rotating it
+            eps_scalar = bool(np.all(eps_packed[:, [1, 2, 4]] == 0)
+                              and np.all(eps_packed[:, 0] == eps_packed[:, 3])
+                              and np.all(eps_packed[:, 0] == eps_packed[:, 5]))
+            eps = eps_packed if eps_scalar else pack_symmetric(q @ unpack_symmetric(eps_packed) @ q.T)
             mu_packed = material.mu_packed(frequency)
             mu_scalar = bool(np.all(mu_packed[:, [1, 2, 4]] == 0)
                              and np.all(mu_packed[:, 0] == mu_packed[:, 3])
@@ -210,6 +216,7 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
             else:
                 lp = LayerPlan(KIND_ANISO_EXIT, kind)
             lp.eps, lp.mu, lp.mu_scalar = np.ascontiguousarray(eps), np.ascontiguousarray(mu), mu_scalar
+            lp.eps_scalar = eps_scalar
             lp.cos_beta, lp.sin_beta, lp.material = cos_b, sin_b, material
         elif kind == TYPE_ISO_EXIT:
             eps_exit = data.get("permittivity")

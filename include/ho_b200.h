@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 3
+#define HO_ABI_VERSION 4
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -60,6 +60,9 @@ typedef struct {
   int32_t mu_scalar;   /* 1: mu = mu[.,0] * I (rotation invariant)  0: full symmetric tensor */
   int32_t n_beta;      /* entries of cos_beta/sin_beta: 1 or B */
   int32_t n_thickness; /* entries of thickness: 1 or T (0 for semi-infinite layers) */
+  int32_t eps_scalar;  /* 1: the crystal is isotropic, eps = eps[.,0] * I at every frequency (e.g. SiC):
+                          with mu_scalar the layer has closed-form modes kz^2 = eps mu - kx^2 and is
+                          evaluated like the isotropic film / exit, no quartic */
   /* packed symmetric tensors (xx,xy,xz,yy,yz,zz) per frequency, already rotated by
      Ry(rotY+1e-8)*Rx(rotX) on the host (layers.py:26-66,283); [n_eps][6], [n_mu][6] */
   const ho_c128* eps;

@@ -143,12 +143,24 @@ def test_descriptor_validation_without_gpu(built_library):
     assert built_library.ho_reflect(ctypes.byref(prob), ctypes.byref(out), 0, 0, None) == -1
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors of the ABI structs vs what a C compiler makes of include/ho_b200.h."""
+    import subprocess
+
     from hyperbolic_optics_b200 import _native as nat
 
-    assert ctypes.sizeof(nat.LayerDesc) == 112
-    assert ctypes.sizeof(nat.Problem) == 64 + 24 * 112
-    assert nat.Problem.layers.offset == 64
+    probe = tmp_path / "probe.c"
+    probe.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "ho_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ho_layer_t), sizeof(ho_problem_t), '
+        'offsetof(ho_problem_t, layers), offsetof(ho_layer_t, eps), offsetof(ho_layer_t, exit_n), '
+        'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_pp)); return 0; }\n')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(nat.LayerDesc), ctypes.sizeof(nat.Problem), nat.Problem.layers.offset,
+                   nat.LayerDesc.eps.offset, nat.LayerDesc.exit_n.offset, ctypes.sizeof(nat.Outputs),
+                   nat.Outputs.t_pp.offset]
 
 
 def test_product_never_imports_oracle():

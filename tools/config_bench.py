@@ -38,6 +38,10 @@ def configs():
                [P.prism(12.5), P.gap(0.5), P.substrate("Quartz", ry=90)], None, 720, ("transfer",), False),
         "c4": ({"type": "FullSweep", "frequency": f410},
                [P.prism(12.5), P.film("hBN", 0.1), P.substrate("SiC")], 512, 480, ("transfer", "scattering"), False),
+        # same film on an anisotropic (un-tilted) substrate: both layers take the general spectral split
+        "c4_aniso": ({"type": "FullSweep", "frequency": f410},
+                     [P.prism(12.5), P.film("hBN", 0.1), P.substrate("Calcite", ry=90)], 512, 480,
+                     ("transfer", "scattering"), False),
         "c4_tilted": ({"type": "FullSweep", "frequency": f410},
                       [P.prism(12.5), P.film("hBN", 0.1, ry=30, rz=10), P.substrate("Quartz", ry=50)], 512, 480,
                       ("transfer", "scattering"), False),
