@@ -235,4 +235,22 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
         plan.layers.append(lp)
     if not plan.layers or plan.layers[-1].kind not in (KIND_ANISO_EXIT, KIND_ISO_EXIT):
         raise ValueError("the stack must end with a semi-infinite exit layer")
+    _collapse_unswept_axes(plan)
     return plan
+
+
+def _collapse_unswept_axes(plan: StackPlan) -> None:
+    """The reference's result shape is the NumPy broadcast of its layer matrices (``structure.py:259-270``):
+    an axis no layer depends on stays size 1 and is squeezed by ``present`` (``axes.py:83-95``).
+    * B (azimuth) enters only through a crystal's z rotation (``layers.py:318-351``; "static" is
+      broadcast to the azimuth grid too);
+    * F enters through ``k0`` of a finite layer (``waves.py:317-326``) or a dispersive tensor.
+    Collapsing such an axis here reproduces the reference's shapes and skips the redundant points."""
+    crystals = [lp for lp in plan.layers if lp.kind in (KIND_ANISO_FILM, KIND_ANISO_EXIT)]
+    if plan.B > 1 and not crystals:
+        plan.B = 1
+    finite = any(lp.kind in (KIND_ISO_FILM, KIND_ANISO_FILM) for lp in plan.layers)
+    dispersive = any(lp.eps.shape[0] > 1 or lp.mu.shape[0] > 1 for lp in crystals)
+    if plan.F > 1 and not (finite or dispersive):
+        plan.F = 1
+        plan.k0 = plan.k0[:1]

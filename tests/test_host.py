@@ -185,3 +185,29 @@ def test_thickness_sweep_argument_errors():
         ThicknessSweep(payload, 0, [0.5])
     with pytest.raises(ValueError):
         ThicknessSweep(payload, 1, [])
+
+
+def test_result_shape_follows_reference_broadcasting():
+    """The reference's result shape is the broadcast of its layer matrices: axes that no layer
+    depends on (azimuth without a crystal, frequency without a finite or dispersive layer) are
+    squeezed away.  The planner collapses the same axes (random stacks of the differential test)."""
+    from tests.test_gpu_random_stacks import random_case
+
+    seen = set()
+    for seed in range(1000, 1080):
+        entry = random_case(seed)
+        inc, az = angle_overrides(entry)
+        try:
+            ref = oracle.run(entry["payload"], backend="scattering", incident_angle=inc, azimuthal_angle=az)
+        except np.linalg.LinAlgError:
+            continue
+        sc = ScenarioSetup(entry["payload"]["ScenarioData"])
+        if inc is not None:
+            sc.incident_angle = inc
+        if az is not None:
+            sc.azimuthal_angle = az
+        plan = planmod.build_plan(sc, entry["payload"]["Layers"])
+        squeezed = tuple(n for n in plan.fabt_shape if n != 1)
+        assert squeezed == np.shape(ref["r_pp"]), f"seed {seed}: {plan.fabt_shape} vs {np.shape(ref['r_pp'])}"
+        seen.add((entry["payload"]["ScenarioData"]["type"], len(squeezed)))
+    assert len(seen) >= 5  # several scenario types and collapsed / full ranks were exercised
