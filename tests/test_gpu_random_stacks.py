@@ -27,6 +27,17 @@ def _angle(rng):
     return float(rng.choice(SPECIAL)) if rng.random() < 0.5 else float(rng.uniform(0.0, 180.0))
 
 
+def _arbitrary(rng, magnetic):
+    """Lossy arbitrary-tensor material (reference materials.py:781-926), optionally with a mu tensor."""
+    def c(lo, hi):
+        return {"real": float(rng.uniform(lo, hi)), "imag": float(rng.uniform(0.05, 1.5))}
+
+    spec = {"eps_xx": c(-8, 8), "eps_yy": c(-8, 8), "eps_zz": c(1, 8), "eps_xy": c(-0.5, 0.5)}
+    if magnetic:
+        spec.update({"mu_xx": c(0.8, 2.0), "mu_yy": c(0.8, 2.0), "mu_zz": c(0.8, 2.0), "mu_xz": c(-0.2, 0.2)})
+    return spec
+
+
 def random_case(seed):
     rng = np.random.default_rng(seed)
     names = list(MATERIALS)
@@ -48,6 +59,15 @@ def random_case(seed):
         layers.append(P.substrate(mats[-1], rx=_angle(rng), ry=_angle(rng), rz=_angle(rng)))
     else:
         layers.append(P.iso_exit(float(rng.uniform(1.0, 12.0))))
+    finite = [i for i, layer in enumerate(layers) if "thickness" in layer]
+    extras = np.random.default_rng(seed + 7919)   # separate stream: keeps the base stacks of earlier seeds
+    if finite and extras.random() < 0.3:           # thickness axis -> thickness-sweep kernel
+        i = finite[int(extras.integers(len(finite)))]
+        layers[i]["thickness"] = [float(x) for x in 10 ** np.sort(extras.uniform(-2, 0.6, int(extras.integers(2, 6))))]
+    crystal = [i for i, layer in enumerate(layers) if "material" in layer]
+    if crystal and extras.random() < 0.25:         # arbitrary (possibly magnetic) tensor -> general-mu kernel
+        i = crystal[int(extras.integers(len(crystal)))]
+        layers[i]["material"] = _arbitrary(extras, magnetic=extras.random() < 0.6)
     kind = ["Incident", "Azimuthal", "Dispersion", "FullSweep"][int(rng.integers(4))]
     n_f = int(rng.integers(2, 6))
     freqs = list(np.sort(rng.uniform(lo, hi, n_f)))
