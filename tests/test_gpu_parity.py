@@ -483,3 +483,62 @@ def test_c5_full_size_properties(built_library):
         assert float((blk[0] - r_amp).abs().max()) <= 1e-9
         assert float((blk.sum(dim=0) - 1.0).abs().max()) <= 1e-12
         assert float(blk[1:].min()) >= -1e-9
+
+
+def test_fresnel_single_interface(built_library):
+    """Analytic anchor independent of LAPACK (reference tests/test_fields.py:98-112): one lossless
+    interface prism | isotropic exit reproduces the Fresnel reflectances and R + T = 1."""
+    from hyperbolic_optics_b200 import FieldProfile, Structure
+
+    n1, n2 = 2.0, 1.5
+    payload = {"ScenarioData": {"type": "Incident", "frequency": [1000.0]},
+               "Layers": [{"type": "Ambient Incident Layer", "permittivity": n1 ** 2},
+                          {"type": "Semi Infinite Isotropic Layer", "permittivity": n2 ** 2}]}
+    for backend in ("transfer", "scattering"):
+        s = Structure(device="cuda:0")
+        s.execute(payload, backend=backend, power=True)
+        th = np.asarray(s.incident_angle)[1:-1]            # skip the grazing end points (1/cos = 1.6e16)
+        ct = np.sqrt((1 - (n1 / n2 * np.sin(th)) ** 2).astype(complex))
+        rs = (n1 * np.cos(th) - n2 * ct) / (n1 * np.cos(th) + n2 * ct)
+        rp = (n2 * np.cos(th) - n1 * ct) / (n2 * np.cos(th) + n1 * ct)
+        np.testing.assert_allclose(np.abs(s.r_ss[1:-1]) ** 2, np.abs(rs) ** 2, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(np.abs(s.r_pp[1:-1]) ** 2, np.abs(rp) ** 2, rtol=0, atol=1e-12)
+        assert float(np.abs(s.r_ps).max()) == 0.0 and float(np.abs(s.r_sp).max()) == 0.0
+        fp = FieldProfile(s)
+        for pol in "ps":
+            np.testing.assert_allclose((fp.reflectance(pol) + fp.transmittance(pol))[1:-1], 1.0, rtol=0, atol=1e-12)
+            assert float(np.min(fp.transmittance(pol)[1:-1])) >= -1e-12
+
+
+def test_lossless_anisotropic_film_conserves_flux(built_library):
+    """A lossless (real-tensor) rotated biaxial film between lossless media: propagating and
+    evanescent modes coexist (the mixed real/complex spectrum on which the reference's slot-wise
+    mode sort breaks).  With the per-eigenvalue forward rule the flux through the film
+    is conserved: no absorption in the film, R + T = 1, R from fluxes equals |r_co|^2 + |r_cross|^2,
+    and the two recursions agree."""
+    from hyperbolic_optics_b200 import FieldProfile, Structure
+
+    film = {"eps_xx": 2.2, "eps_yy": 3.1, "eps_zz": 4.3, "eps_xy": 0.0, "eps_xz": 0.0, "eps_yz": 0.0}
+    payload = {"ScenarioData": {"type": "Dispersion", "frequency": 1000.0},
+               "Layers": [{"type": "Ambient Incident Layer", "permittivity": 6.0},
+                          {"type": "Crystal Layer", "material": film, "thickness": 1.3,
+                           "rotationX": 20, "rotationY": 35, "rotationZ": 10},
+                          {"type": "Semi Infinite Isotropic Layer", "permittivity": 2.0}]}
+    res = {}
+    for backend in ("transfer", "scattering"):
+        s = Structure(device="cuda:0")
+        s.execute(payload, backend=backend, power=True)
+        res[backend] = s
+        fp = FieldProfile(s)
+        inner = (slice(1, -1), slice(None))                 # away from normal / grazing end points
+        for pol, (co, cross) in (("p", ("r_pp", "r_ps")), ("s", ("r_ss", "r_sp"))):
+            summ = fp.summary(pol)
+            a_film = np.asarray(summ["layers"][0]["absorptance"])[inner]
+            assert float(np.abs(a_film).max()) <= 1e-9, f"{backend}/{pol}: film absorbs {np.abs(a_film).max():.2e}"
+            r_amp = (np.abs(getattr(s, co)) ** 2 + np.abs(getattr(s, cross)) ** 2)[inner]
+            np.testing.assert_allclose(np.asarray(summ["R"])[inner], r_amp, rtol=0, atol=1e-9)
+            assert float(np.min(np.asarray(summ["T"])[inner])) >= -1e-9
+            assert float(np.max(r_amp)) <= 1.0 + 1e-9
+    err = parity.jones_error({k: getattr(res["transfer"], k) for k in parity.R_KEYS},
+                             {k: getattr(res["scattering"], k) for k in parity.R_KEYS})
+    assert float(np.nanmax(err[1:-1])) <= 1e-9
