@@ -683,25 +683,27 @@ template <typename T, bool NM> __device__ __forceinline__ void exit_mode_basis(c
   inv2(b00, b01, b10, b11, binv[0], binv[1], binv[2], binv[3]);
 }
 
-// Mueller matrix M = Re(A F A^-1), F = J (x) J* in the reference's layout (mueller.py:266-307)
+// Mueller matrix M = Re(A F A^-1), F = J (x) J* in the reference's layout (mueller.py:266-307),
+// with the products written out: a = r_pp, b = r_ps, c = r_sp, d = r_ss,
+//   row 0: (|a|^2+|b|^2+|c|^2+|d|^2)/2, (|a|^2-|b|^2+|c|^2-|d|^2)/2,  Re(ab*+cd*),  Im(ab*+cd*)
+//   row 1: (|a|^2+|b|^2-|c|^2-|d|^2)/2, (|a|^2-|b|^2-|c|^2+|d|^2)/2,  Re(ab*-cd*),  Im(ab*-cd*)
+//   row 2:  Re(ac*+bd*),                 Re(ac*-bd*),                  Re(ad*+bc*),  Im(ad*-bc*)
+//   row 3: -Im(ac*+bd*),                -Im(ac*-bd*),                 -Im(ad*+bc*),  Re(ad*-bc*)
+// (six complex products instead of the sixteen entries of F).
 template <typename T> __device__ __forceinline__ void mueller_from_jones(cx<T> pp, cx<T> ps, cx<T> sp, cx<T> ss, T M[16]) {
-  cx<T> F[4][4];
-  F[0][0] = pp * conj(pp); F[0][1] = pp * conj(ps); F[0][2] = ps * conj(pp); F[0][3] = ps * conj(ps);
-  F[1][0] = pp * conj(sp); F[1][1] = pp * conj(ss); F[1][2] = ps * conj(sp); F[1][3] = ps * conj(ss);
-  F[2][0] = sp * conj(pp); F[2][1] = sp * conj(ps); F[2][2] = ss * conj(pp); F[2][3] = ss * conj(ps);
-  F[3][0] = sp * conj(sp); F[3][1] = sp * conj(ss); F[3][2] = ss * conj(sp); F[3][3] = ss * conj(ss);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    cx<T> c0, c1, c2, c3;
-    if (r == 0) { c0 = F[0][0] + F[3][0]; c1 = F[0][1] + F[3][1]; c2 = F[0][2] + F[3][2]; c3 = F[0][3] + F[3][3]; }
-    else if (r == 1) { c0 = F[0][0] - F[3][0]; c1 = F[0][1] - F[3][1]; c2 = F[0][2] - F[3][2]; c3 = F[0][3] - F[3][3]; }
-    else if (r == 2) { c0 = F[1][0] + F[2][0]; c1 = F[1][1] + F[2][1]; c2 = F[1][2] + F[2][2]; c3 = F[1][3] + F[2][3]; }
-    else { c0 = mul_i(F[1][0] - F[2][0]); c1 = mul_i(F[1][1] - F[2][1]); c2 = mul_i(F[1][2] - F[2][2]); c3 = mul_i(F[1][3] - F[2][3]); }
-    M[4 * r + 0] = T(0.5) * (c0.re + c3.re);
-    M[4 * r + 1] = T(0.5) * (c0.re - c3.re);
-    M[4 * r + 2] = T(0.5) * (c1.re + c2.re);
-    M[4 * r + 3] = T(0.5) * (c1.im - c2.im);  // Re(0.5 i (c2 - c1))
-  }
+  const T na = norm2(pp), nb = norm2(ps), nc = norm2(sp), nd = norm2(ss);
+  const cx<T> ab = cmulc(ps, pp), cd = cmulc(ss, sp);   // a b*, c d*   (cmulc(x, y) = conj(x) y)
+  const cx<T> ac = cmulc(sp, pp), bd = cmulc(ss, ps);   // a c*, b d*
+  const cx<T> ad = cmulc(ss, pp), bc = cmulc(sp, ps);   // a d*, b c*
+  const T h = T(0.5);
+  M[0] = h * ((na + nb) + (nc + nd)); M[1] = h * ((na - nb) + (nc - nd));
+  M[2] = ab.re + cd.re;               M[3] = ab.im + cd.im;
+  M[4] = h * ((na + nb) - (nc + nd)); M[5] = h * ((na - nb) - (nc - nd));
+  M[6] = ab.re - cd.re;               M[7] = ab.im - cd.im;
+  M[8] = ac.re + bd.re;               M[9] = ac.re - bd.re;
+  M[10] = ad.re + bc.re;              M[11] = ad.im - bc.im;
+  M[12] = -(ac.im + bd.im);           M[13] = bd.im - ac.im;
+  M[14] = -(ad.im + bc.im);           M[15] = ad.re - bc.re;
 }
 
 }  // namespace ho
