@@ -151,3 +151,47 @@ def test_random_stacks_match_oracle(block, built_library):
         n_trusted += int(mask.sum())
     print(f"block {block}: {n_points} points, worst Jones rel err scattering {worst_s:.2e}, "
           f"transfer {worst_t:.2e} on {n_trusted} trusted points")
+
+
+def extreme_case(seed):
+    """Stacks at the edges: films up to 300 um (growth exponents of several hundred -- the transfer
+    product overflows, the stable recursion must not), frequencies on the TO resonances (|eps| of
+    several hundred), near-normal and near-grazing incidence in the Simple scenario."""
+    rng = np.random.default_rng(seed)
+    resonant = {"hBN": [1370.0, 1610.0, 780.0, 830.0], "SiC": [797.0, 970.0], "Quartz": [450.0, 509.0, 538.0],
+                "Calcite": [1410.0, 1550.0], "AlN": [611.0, 670.0, 890.0]}
+    names = list(resonant)
+    m_film, m_sub = names[int(rng.integers(len(names)))], names[int(rng.integers(len(names)))]
+    freq = float(rng.choice(resonant[m_film])) + float(rng.uniform(-2.0, 2.0))
+    layers = [P.prism(float(rng.uniform(5.0, 50.0))),
+              P.gap(float(10 ** rng.uniform(-1, 2.5)), 1.0),
+              P.film(m_film, float(10 ** rng.uniform(-1, 2.5)), rx=_angle(rng), ry=_angle(rng), rz=_angle(rng)),
+              P.substrate(m_sub, ry=_angle(rng)) if rng.random() < 0.7 else P.iso_exit(float(rng.uniform(1.0, 12.0)))]
+    theta = float(rng.choice([0.0, 1e-6, 89.999999, 45.0])) if rng.random() < 0.5 else float(rng.uniform(0.0, 90.0))
+    sd = {"type": "Simple", "incidentAngle": theta, "azimuthal_angle": float(rng.uniform(0.0, 360.0)), "frequency": freq}
+    return {"payload": {"ScenarioData": sd, "Layers": layers}, "grid": None}
+
+
+def test_extreme_stacks_stable_backend(built_library):
+    """The stable recursion vs the reference's scattering backend on 120 edge-case points."""
+    from oracle import reference_port as oracle
+
+    worst, compared = 0.0, 0
+    for seed in range(5000, 5120):
+        entry = extreme_case(seed)
+        try:
+            ref = oracle.run(entry["payload"], backend="scattering")
+        except np.linalg.LinAlgError:
+            continue
+        s = _gpu(entry, "scattering")
+        got = {k: getattr(s, k) for k in parity.R_KEYS}
+        assert all(np.isfinite(got[k]) for k in parity.R_KEYS), f"seed {seed}: non-finite\n{entry['payload']}"
+        err = float(parity.jones_error(got, ref))
+        if not np.isfinite(err):
+            continue  # the reference itself is non-finite here
+        assert err <= 1e-8, f"seed {seed}: {err:.3e}\n{entry['payload']}"
+        refl = abs(got["r_pp"]) ** 2 + abs(got["r_ps"]) ** 2
+        assert refl <= 1.0 + 1e-9
+        worst, compared = max(worst, err), compared + 1
+    assert compared >= 100
+    print(f"extreme stacks: {compared} points compared, worst Jones rel err {worst:.2e}")
