@@ -344,6 +344,7 @@ class Layer:
         self.kind = kind
         self.matrix = None
         self.modes = None  # (V, kz) for Wave-built layers
+        self.tensors = None  # (eps, mu) rotated, canonical [A|1, B|1, F|1, 1, 3, 3], for Wave-built layers
         self.thickness = None
         self.eps_exit = None
 
@@ -420,6 +421,7 @@ def build_stack(payload, incident_angle=None, azimuthal_angle=None):
             mu = lift(np.eye(3, dtype=np.complex128) * m, (), 2)
             v, kz = sorted_modes(kx, eps, mu)
             layer.modes = (v, kz)
+            layer.tensors = (eps, mu)
             layer.matrix = finite_layer_matrix(v, kz, k0, layer.thickness)
         elif kind in (LAYER_CRYSTAL, LAYER_CRYSTAL_EXIT):
             eps, mu = material_tensors(data.get("material"), frequency)
@@ -430,6 +432,7 @@ def build_stack(payload, incident_angle=None, azimuthal_angle=None):
             mu = rot @ _canonical_tensor(mu.astype(np.complex128)) @ rot_t
             v, kz = sorted_modes(kx, eps, mu)
             layer.modes = (v, kz)
+            layer.tensors = (eps, mu)
             if kind == LAYER_CRYSTAL:
                 layer.matrix = finite_layer_matrix(v, kz, k0, layer.thickness)
             else:

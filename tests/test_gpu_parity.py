@@ -542,3 +542,56 @@ def test_lossless_anisotropic_film_conserves_flux(built_library):
     err = parity.jones_error({k: getattr(res["transfer"], k) for k in parity.R_KEYS},
                              {k: getattr(res["scattering"], k) for k in parity.R_KEYS})
     assert float(np.nanmax(err[1:-1])) <= 1e-9
+
+
+def test_thick_evanescent_stack_vs_high_precision_truth(built_library):
+    """BASELINE config 5's regime: the 11-layer lossy stack behind an evanescent gap swept to 250 um.
+    The reference's float64 transfer product is noise or overflows there and its FieldProfile cannot
+    run under the scattering backend (fields.py:87-88); the arbiter is the same formulas in
+    arbitrary precision (oracle/mp_reference.py).  r_ij and R, T, A_i of the stable recursion +
+    thickness-sweep kernel must match it."""
+    from hyperbolic_optics_b200 import FieldProfile, Structure
+    from oracle import mp_reference
+    from oracle import reference_port as oracle
+
+    payload = {"ScenarioData": {"type": "Incident", "frequency": [650.0, 800.0, 935.0]},
+               "Layers": P_LAYERS_C5([0.1, 2.0, 20.0, 60.0, 250.0])}
+    inc = np.linspace(-np.pi / 2 + 1e-9, np.pi / 2 - 1e-9, 9)
+    s = Structure(device="cuda:0")
+    s.get_scenario(payload["ScenarioData"])
+    s.scenario.incident_angle = inc
+    s.setup_attributes()
+    s.get_layers(payload["Layers"])
+    s.with_power = True
+    s.calculate_scattering()
+    fp = FieldProfile(s)
+    with np.errstate(all="ignore"):
+        port_t = oracle.run(payload, backend="transfer", incident_angle=inc)
+    noisy = 0
+    worst_r = worst_p = 0.0
+    for f in range(3):
+        for a in (1, 2, 4, 6, 7):
+            for t in range(5):
+                truth = mp_reference.point(payload, (a, 0, f, t), incident_angle=inc)
+                got = {k: getattr(s, k)[f, a, t] for k in parity.R_KEYS}
+                num = sum(abs(got[k] - truth[k]) ** 2 for k in parity.R_KEYS)
+                den = sum(abs(truth[k]) ** 2 for k in parity.R_KEYS)
+                worst_r = max(worst_r, float(np.sqrt(num / den)))
+                with np.errstate(all="ignore"):
+                    pt = sum(abs(port_t[k][f, a, t] - truth[k]) ** 2 for k in parity.R_KEYS) / den
+                noisy += int(not np.isfinite(pt) or np.sqrt(pt) > 1e-10)
+                for pol in "ps":
+                    summ = fp.summary(pol)
+                    worst_p = max(worst_p, abs(float(summ["R"][f, a, t]) - truth[f"R_{pol}"]),
+                                  abs(float(summ["T"][f, a, t]) - truth[f"T_{pol}"]),
+                                  max(abs(float(rec["absorptance"][f, a, t]) - x)
+                                      for rec, x in zip(summ["layers"], truth[f"A_{pol}"])))
+    assert noisy >= 15, "the case is meant to sit where the float64 transfer product is noise or overflows"
+    assert worst_r <= 1e-10, f"Jones rel err vs high-precision truth {worst_r:.3e}"
+    assert worst_p <= 1e-10, f"power abs err vs high-precision truth {worst_p:.3e}"
+
+
+def P_LAYERS_C5(thicknesses):
+    from tests.golden.payloads import config5_layers
+
+    return config5_layers(thicknesses)

@@ -99,3 +99,32 @@ def test_oracle_vs_reference_goldens(name):
     for k in parity.R_KEYS:
         np.testing.assert_allclose(sub(out[k], 0), golden[k], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(sub(out["mueller"], 2), golden["mueller"], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,idx", [("c5_thickness_11layer", (3, 0, 2, 1)), ("c5_thickness_11layer", (7, 0, 6, 7)),
+                                      ("dispersion_iso_exit", (5, 7, 0, 0)), ("c4_fullsweep_hbn_sic", (3, 4, 20, 0)),
+                                      ("thickness_axis_film", (11, 0, 3, 5))])
+def test_high_precision_restatement_pins_the_port(name, idx):
+    """oracle/mp_reference.py (the reference's transfer formulas in 50+ digit arithmetic on the
+    same float64 inputs) vs the NumPy port's stable backend: the two independent restatements agree
+    to rounding, so the mpmath one can arbitrate where float64 transfer products are noise."""
+    from oracle import mp_reference
+    from tests.golden.payloads import ALL, angle_overrides
+
+    entry = ALL[name]
+    inc, az = angle_overrides(entry)
+    ref = oracle.run(entry["payload"], backend="scattering", incident_angle=inc, azimuthal_angle=az)
+    truth = mp_reference.point(entry["payload"], idx, inc, az)
+    a, b, f, t = idx
+    pres = tuple(i for i, n in zip((f, a, b, t), _canonical_sizes(ref["stack"])) if n > 1)
+    num = sum(abs(truth[k] - ref[k][pres]) ** 2 for k in ("r_pp", "r_ps", "r_sp", "r_ss"))
+    den = sum(abs(ref[k][pres]) ** 2 for k in ("r_pp", "r_ps", "r_sp", "r_ss"))
+    assert np.sqrt(num / den) <= 1e-13
+    assert abs(truth["R_p"] + truth["T_p"] + sum(truth["A_p"]) - 1.0) <= 1e-13
+
+
+def _canonical_sizes(stack):
+    """(F, A, B, T) sizes of a port stack."""
+    thick = [np.size(l.thickness) for l in stack["layers"] if l.thickness is not None]
+    return (np.size(stack["frequency"]), np.size(stack["inc"]),
+            np.size(stack["az"]) if stack["az"] is not None else 1, max(thick, default=1))
