@@ -90,24 +90,25 @@ template <typename T, bool STABLE, bool NM, bool EXTRAS>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
                                             ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4]) {
   using namespace ho;
+  // isotropic crystal (scalar eps(f), mu(f), e.g. SiC): closed-form modes, no quartic
+  const bool iso_crystal = (L.kind == HO_ANISO_FILM || L.kind == HO_ANISO_EXIT) && L.eps_scalar && L.mu_scalar;
   if (L.kind == HO_ISO_EXIT) {
     exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
     if constexpr (EXTRAS) { binv[0] = mk<T>(T(1), T(0)); binv[1] = mk<T>(T(0), T(0)); binv[2] = binv[1]; binv[3] = binv[0]; }
-  } else if (L.kind == HO_ISO_FILM) {
-    const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-    const cx<T> c = mk<T>(T(0), -(k0 * d));  // -i k0 d   (reference waves.py:326)
-    iso_film(k, mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mk<T>(T(L.iso_mu.re), T(L.iso_mu.im)), c, STABLE, y0, y1, w);
-  } else if (L.eps_scalar && L.mu_scalar) {
-    // isotropic crystal (scalar eps(f), mu(f), e.g. SiC): closed-form modes, no quartic
-    const cx<T> eps = ldc<T>(L.eps + 6 * (int64_t)(L.n_eps > 1 ? f : 0));
-    const cx<T> mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
+  } else if (L.kind == HO_ISO_FILM || iso_crystal) {
+    // scalar medium: constants of the descriptor (isotropic film) or row f of the tables (crystal)
+    cx<T> eps = mk<T>(T(L.iso_eps.re), T(L.iso_eps.im)), mu = mk<T>(T(L.iso_mu.re), T(L.iso_mu.im));
+    if (iso_crystal) {
+      eps = ldc<T>(L.eps + 6 * (int64_t)(L.n_eps > 1 ? f : 0));
+      mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
+    }
     if (L.kind == HO_ANISO_EXIT) {
       iso_crystal_exit_plane(k, eps, mu, y0, y1);
       // transmission amplitudes of a degenerate exit: (Ex, Ey) of the transmitted field, as in exit_mode_basis
       if constexpr (EXTRAS) { binv[0] = y0.v0; binv[1] = y1.v0; binv[2] = y0.v1; binv[3] = y1.v1; }
     } else {
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-      iso_film(k, eps, mu, mk<T>(T(0), -(k0 * d)), STABLE, y0, y1, w);
+      iso_film(k, eps, mu, mk<T>(T(0), -(k0 * d)), STABLE, y0, y1, w);  // c = -i k0 d (reference waves.py:326)
     }
   } else {
     // crystal film or crystal exit: one instance of the Delta assembly + spectral split
