@@ -76,6 +76,7 @@ class StackPlan:
     azimuthal_angle: object = None
     frequency: np.ndarray | None = None
     eps_prism: float | None = None
+    k0_all: np.ndarray | None = None   # 2 pi f for every requested frequency (k0 may be collapsed to one entry)
 
     @property
     def n_points(self):
@@ -246,6 +247,7 @@ def _collapse_unswept_axes(plan: StackPlan) -> None:
       broadcast to the azimuth grid too);
     * F enters through ``k0`` of a finite layer (``waves.py:317-326``) or a dispersive tensor.
     Collapsing such an axis here reproduces the reference's shapes and skips the redundant points."""
+    plan.k0_all = plan.k0
     crystals = [lp for lp in plan.layers if lp.kind in (KIND_ANISO_FILM, KIND_ANISO_EXIT)]
     if plan.B > 1 and not crystals:
         plan.B = 1

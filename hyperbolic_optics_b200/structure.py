@@ -97,7 +97,13 @@ class Structure:
         self.eps_prism = self.plan.eps_prism
         self.frequency = self.plan.frequency
         self.k_x = self.plan.kx.reshape(-1, 1, 1, 1)
-        self.k_0 = self.plan.k0.reshape(1, 1, -1, 1)
+        self.k_0 = self.plan.k0_all.reshape(1, 1, -1, 1)
+
+    def display_layer_info(self):
+        """Print the stack top to bottom (reference ``structure.py:349-355``)."""
+        for index, layer in enumerate(self.layers):
+            thickness = getattr(layer, "thickness", None)
+            print(f"Layer {index}: {layer.type}" + ("" if thickness is None else f", thickness {np.ravel(thickness)} cm"))
 
     def calculate(self):
         """Transfer backend selected; the product itself is fused into the kernel launch."""
