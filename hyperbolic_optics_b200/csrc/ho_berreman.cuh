@@ -405,6 +405,21 @@ template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> lam_
   o1 = axpy(dd, r1, scale(phi_s, z1));
 }
 
+// Coefficients of E(x) = alpha_b(x) + (alpha_f(x) - alpha_b(x)) q_b(x) h(x) mod q_f(x) q_b(x), with
+// alpha(x) = (phi_s - dd lam_s) + dd x the linear interpolant of exp(c x) on each root pair
+template <typename T> __device__ __forceinline__ void cubic_coeffs(const Spectrum<T>& s, cx<T> h0, cx<T> h1, cx<T> lf, cx<T> phf, cx<T> ddf,
+                                                                  cx<T> lb, cx<T> phb, cx<T> ddb, cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+  cx<T> ab0 = phb - ddb * lb;
+  cx<T> d0 = (phf - ddf * lf) - ab0, d1 = ddf - ddb;
+  cx<T> g0 = d0 * h0, g1 = fma(d1, h0, d0 * h1), g2 = d1 * h1;
+  // q_f q_b = x^4 + c3 x^3 + c2 x^2 + c1 x + c0
+  cx<T> c3 = -(s.sf + s.sb), c2 = fma(s.sf, s.sb, s.pf + s.pb), c1 = -fma(s.sf, s.pb, s.sb * s.pf), c0 = s.pf * s.pb;
+  a3 = g1 - g2 * (s.sb + c3);
+  a2 = fma(g2, s.pb - c2, g0 - s.sb * g1);
+  a1 = fma(s.pb, g1, ddb - s.sb * g0) - g2 * c1;
+  a0 = fma(s.pb, g0, ab0) - g2 * c0;
+}
+
 // y <- (a0 + a1 D + a2 D^2 + a3 D^3) y: three mat-vecs, one accumulator
 template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const Delta<T, NM>& D, cx<T> a0, cx<T> a1, cx<T> a2, cx<T> a3, Vec4<T>& y) {
   Vec4<T> v = matvec(D, y);
@@ -432,16 +447,8 @@ template <typename T, bool NM> __device__ __forceinline__ void film_transfer(con
   pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
   pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
   if (gf < T(3) && gb < T(3)) {
-    // alpha(x) = (phi_s - dd lam_s) + dd x on each pair
-    cx<T> ab0 = phb - ddb * lb;
-    cx<T> d0 = (phf - ddf * lf) - ab0, d1 = ddf - ddb;
-    cx<T> g0 = d0 * h0, g1 = fma(d1, h0, d0 * h1), g2 = d1 * h1;
-    // q_f q_b = x^4 + c3 x^3 + c2 x^2 + c1 x + c0
-    cx<T> c3 = -(s.sf + s.sb), c2 = fma(s.sf, s.sb, s.pf + s.pb), c1 = -fma(s.sf, s.pb, s.sb * s.pf), c0 = s.pf * s.pb;
-    cx<T> a3 = g1 - g2 * (s.sb + c3);
-    cx<T> a2 = fma(g2, s.pb - c2, g0 - s.sb * g1);
-    cx<T> a1 = fma(s.pb, g1, ddb - s.sb * g0) - g2 * c1;
-    cx<T> a0 = fma(s.pb, g0, ab0) - g2 * c0;
+    cx<T> a0, a1, a2, a3;
+    cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
     cubic_apply(D, a0, a1, a2, a3, y0);
     cubic_apply(D, a0, a1, a2, a3, y1);
     return;
@@ -475,6 +482,27 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 template <typename T, bool NM> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
+  // Thin film (all four |Re(c lambda)| < 3): nothing can overflow and the four exponentials are
+  // within e^6 of each other, so the plane is propagated by the same cubic polynomial as in the
+  // transfer recursion and only re-based to unit (Ex, Ey) rows afterwards -- the re-basing keeps
+  // the basis well conditioned, so the <= 2.6 digits the cubic costs do not compound over
+  // layers.  W is the re-basing matrix.
+  cx<T> lf, phf, ddf, lb, phb, ddb;
+  bool sepf, sepb;
+  T gf, gb;
+  pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
+  pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
+  if (gf < T(3) && gb < T(3)) {
+    cx<T> a0, a1, a2, a3;
+    cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
+    cubic_apply(D, a0, a1, a2, a3, y0);
+    cubic_apply(D, a0, a1, a2, a3, y1);
+    inv2(y0.v0, y1.v0, y0.v1, y1.v1, w[0], w[1], w[2], w[3]);
+    Vec4<T> t0 = axpy(w[2], y1, scale(w[0], y0));
+    y1 = axpy(w[3], y1, scale(w[1], y0));
+    y0 = t0;
+    return;
+  }
   Vec4<T> dy;
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy);
@@ -490,10 +518,9 @@ template <typename T, bool NM> __device__ __forceinline__ void film_stable(const
   pair_modes(s.sf, s.pf, -c, lam, phi, dd, sep, growth);
   Vec4<T> g0 = lin_apply(phi, dd, lam, xf0, matvec(D, xf0));
   Vec4<T> g1 = lin_apply(phi, dd, lam, xf1, matvec(D, xf1));
-  // exp(+c K_b) X_b: backward modes up the film, decaying
-  pair_modes(s.sb, s.pb, c, lam, phi, dd, sep, growth);
-  Vec4<T> e0 = lin_apply(phi, dd, lam, xb0, matvec(D, xb0));
-  Vec4<T> e1 = lin_apply(phi, dd, lam, xb1, matvec(D, xb1));
+  // exp(+c K_b) X_b: backward modes up the film, decaying (modes of the pair already known)
+  Vec4<T> e0 = lin_apply(phb, ddb, lb, xb0, matvec(D, xb0));
+  Vec4<T> e1 = lin_apply(phb, ddb, lb, xb1, matvec(D, xb1));
   y0 = axpy(g0.v1, e1, axpy(g0.v0, e0, xf0));
   y1 = axpy(g1.v1, e1, axpy(g1.v0, e0, xf1));
   w[0] = fma(n01, g0.v1, n00 * g0.v0); w[1] = fma(n01, g1.v1, n00 * g1.v0);

@@ -435,7 +435,24 @@ def _inv2(m00, m01, m10, m11):
     return m11 * idet, -m01 * idet, -m10 * idet, m00 * idet
 
 
-def film_stable(D, Y, spec, cfac, rows=(0, 1), return_w=False):
+def film_stable(D, Y, spec, cfac, rows=(0, 1), return_w=False, mono=True):
+    """Stable propagation; thin films (MONO_GROWTH) use the cubic of the transfer recursion followed
+    by a re-basing to unit E rows, thick films the decaying-exponential block form."""
+    block, w_block = _film_stable_block(D, Y, spec, cfac, rows)
+    if mono:
+        raw = film_transfer_mono(D, Y, spec, cfac)
+        r0, r1 = rows
+        n00, n01, n10, n11 = _inv2(raw[0][r0], raw[1][r0], raw[0][r1], raw[1][r1])
+        thin_y = [tuple(raw[0][i] * n00 + raw[1][i] * n10 for i in range(4)),
+                  tuple(raw[0][i] * n01 + raw[1][i] * n11 for i in range(4))]
+        thin_w = ((n00, n01), (n10, n11))
+        thin = film_growth(spec, cfac) < MONO_GROWTH
+        block = [tuple(np.where(thin, thin_y[k][i], block[k][i]) for i in range(4)) for k in range(2)]
+        w_block = tuple(tuple(np.where(thin, thin_w[r][c], w_block[r][c]) for c in range(2)) for r in range(2))
+    return (block, w_block) if return_w else block
+
+
+def _film_stable_block(D, Y, spec, cfac, rows=(0, 1), return_w=True):
     """Stable (scattering-equivalent) propagation of the plane spanned by Y through a film.
 
     Returns the renormalised plane X_f + G_b Z_b N (L G_f^-1 X_f) using only decaying
