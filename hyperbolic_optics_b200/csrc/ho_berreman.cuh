@@ -375,8 +375,8 @@ template <typename T> __device__ __forceinline__ void pair_modes(cx<T> s, cx<T> 
   phi_s = cexp(cs);
   cx<T> x = T(2) * (c * h);
   separated = x.re > T(1);
-  if (norm2(x) < T(0.25)) {
-    dd = c * phi_s * expm1c(x);
+  if (norm2(x) < T(0.01)) {
+    dd = c * phi_s * expm1c_small(x);
   } else {
     dd = (cexp(c * lam_g) - phi_s) / (lam_g - lam_s);
   }
