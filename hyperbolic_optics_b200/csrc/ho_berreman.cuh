@@ -420,6 +420,14 @@ template <typename T> __device__ __forceinline__ void cubic_coeffs(const Spectru
   a0 = fma(s.pb, g0, ab0) - g2 * c0;
 }
 
+// Thin-film switch of both recursions: all four |Re(c lambda)| below this.  The cubic mixes the four
+// exponentials and costs log10 of their ratio in digits: e^6 (2.6 of 16 digits) in complex128,
+// e^3 (1.3 of 7) in the opt-in complex64 kernels.
+template <typename T> __device__ __forceinline__ bool thin_film(T gf, T gb) {
+  const T limit = sizeof(T) == 8 ? T(3) : T(1.5);
+  return gf < limit && gb < limit;
+}
+
 // y <- (a0 + a1 D + a2 D^2 + a3 D^3) y: three mat-vecs, one accumulator
 template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const Delta<T, NM>& D, cx<T> a0, cx<T> a1, cx<T> a2, cx<T> a3, Vec4<T>& y) {
   Vec4<T> v = matvec(D, y);
@@ -446,7 +454,7 @@ template <typename T, bool NM> __device__ __forceinline__ void film_transfer(con
   T gf, gb;
   pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
   pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
-  if (gf < T(3) && gb < T(3)) {
+  if (thin_film(gf, gb)) {
     cx<T> a0, a1, a2, a3;
     cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
     cubic_apply(D, a0, a1, a2, a3, y0);
@@ -492,7 +500,7 @@ template <typename T, bool NM> __device__ __forceinline__ void film_stable(const
   T gf, gb;
   pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
   pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
-  if (gf < T(3) && gb < T(3)) {
+  if (thin_film(gf, gb)) {
     cx<T> a0, a1, a2, a3;
     cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
     cubic_apply(D, a0, a1, a2, a3, y0);
