@@ -12,8 +12,9 @@ same errors (``ValueError`` for an unknown backend / layer type / second swept t
 ``NotImplementedError`` for an unknown scenario or material).  Numerical failure is not an
 error: the transfer backend returns inf/NaN where the reference's 4x4 product overflows.
 
-Additions (all optional): ``mueller`` (the sample Mueller matrix, fused into the same
-kernel), ``stokes`` for a given incident Stokes vector, ``power=True`` (R, T and layer-resolved
+Additions (all optional): ``shard=(rank, world_size)`` (one process per GPU: this process
+computes -- and returns -- only its contiguous slab of the slowest swept axis, ``sharding.py``),
+``mueller`` (the sample Mueller matrix, fused into the same kernel), ``stokes`` for a given incident Stokes vector, ``power=True`` (R, T and layer-resolved
 absorption for p and s incidence from the same launch, both backends; consumed by
 ``hyperbolic_optics_b200.FieldProfile``), ``device=`` / ``keep_on_device=``.
 
@@ -27,7 +28,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import engine
+from . import engine, sharding
 from .plan import StackPlan, build_plan
 from .scenario import ScenarioSetup, present
 
@@ -77,6 +78,8 @@ class Structure:
         self.own_results = True
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.shard = None          # (rank, world_size) or None
+        self.point_range = None    # [n_begin, n_end) of the presentation-ordered grid this run computed
         self._backend = "transfer"
         self._last_backend = "transfer"
 
@@ -128,7 +131,7 @@ class Structure:
 
     # -- one-call protocol ---------------------------------------------------------------
     def execute(self, payload, backend="transfer", mueller=True, incident_stokes=None,
-                keep_on_device=False, own_results=None, power=False, transmission=False):
+                keep_on_device=False, own_results=None, power=False, transmission=False, shard=None):
         if backend not in ("transfer", "scattering"):
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
         self.with_mueller = bool(mueller)
@@ -138,6 +141,12 @@ class Structure:
         self.keep_on_device = bool(keep_on_device)
         if own_results is not None:
             self.own_results = bool(own_results)
+        if shard is not None:
+            rank, world = (int(x) for x in shard)
+            if not 0 <= rank < world:
+                raise ValueError(f"shard=(rank, world_size) needs 0 <= rank < world_size, got {shard!r}")
+            shard = (rank, world)
+        self.shard = shard
         self.get_scenario(payload.get("ScenarioData"))
         self.get_layers(payload.get("Layers", None))
         self._run(backend)
@@ -148,14 +157,21 @@ class Structure:
         plan = self.plan
         prob = engine.DeviceProblem(plan, backend, self.device)
         self.h2d_bytes = prob.h2d_bytes
-        n = plan.n_points
-        shape = plan.fabt_shape
+        # multi-GPU: this process owns a contiguous slab of the slowest swept axis (no exchange step)
+        base, n, shape = 0, plan.n_points, plan.fabt_shape
+        if self.shard is not None:
+            rank, world = self.shard
+            base, stop_all = sharding.point_range(plan, world, rank)
+            n, shape = stop_all - base, sharding.slab_shape(plan, world, rank)
+        self.point_range = (base, base + n)
+        if n == 0:
+            raise ValueError(f"shard {self.shard}: more ranks than samples of the sharded axis")
         want_stokes = self.incident_stokes is not None
         planes = 2 * (len(plan.layers) + 1) if self.with_power else 0
         if self.keep_on_device:
             out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
                                        transmission=self.with_transmission)
-            engine.reflect(prob, out)
+            engine.reflect(prob, out, base, base + n)
             r = out.r.reshape((4,) + shape)
             self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False)
             self.d2h_bytes = 0
@@ -178,7 +194,7 @@ class Structure:
             buf = bufs[ci % len(bufs)]
             if done[ci % len(bufs)] is not None:
                 compute.wait_event(done[ci % len(bufs)])  # previous D2H out of this buffer finished
-            engine.reflect(prob, buf, start, stop, stream=compute)
+            engine.reflect(prob, buf, base + start, base + stop, stream=compute)
             ready = torch.cuda.Event()
             ready.record(compute)
             copy.wait_event(ready)

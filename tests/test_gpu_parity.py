@@ -595,3 +595,32 @@ def P_LAYERS_C5(thicknesses):
     from tests.golden.payloads import config5_layers
 
     return config5_layers(thicknesses)
+
+
+@pytest.mark.parametrize("name", ["c4_fullsweep_hbn_sic", "c5_thickness_11layer", "c2_dispersion_moo3"])
+def test_sharded_execute_tiles_the_full_result(name, built_library):
+    """Structure.execute(..., shard=(rank, world)): every rank returns its contiguous slab of the
+    slowest swept axis; stacking the slabs reproduces the unsharded run bit for bit (the multi-GPU
+    path of bench.py, one process per GPU, no data-path collective)."""
+    from hyperbolic_optics_b200 import Structure
+
+    entry = ALL[name]
+    payload = {"ScenarioData": dict(entry["payload"]["ScenarioData"]), "Layers": entry["payload"]["Layers"]}
+    grid = entry.get("grid") or {}
+    if "A" in grid:
+        payload["ScenarioData"]["n_incident"] = grid["A"]
+    if "B" in grid:
+        payload["ScenarioData"]["n_azimuthal"] = grid["B"]
+    full = Structure(device="cuda:0")
+    full.execute(payload, backend="scattering", power=True)
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            s = Structure(device="cuda:0")
+            s.execute(payload, backend="scattering", power=True, shard=(rank, world))
+            assert s.point_range[1] - s.point_range[0] == s.r_pp.size
+            parts.append(s)
+        for key in parity.R_KEYS + ("mueller",):
+            np.testing.assert_array_equal(np.concatenate([getattr(p, key) for p in parts], axis=0), getattr(full, key))
+        np.testing.assert_array_equal(np.concatenate([p.power["p"]["R"] for p in parts], axis=0), full.power["p"]["R"])
+        assert parts[0].point_range[0] == 0 and parts[-1].point_range[1] == full.plan.n_points
