@@ -92,6 +92,16 @@ class DeviceProblem:
         self._c128.append(np.asarray(arr))
         return ("c", off)
 
+    def with_backend(self, backend):
+        """Same resident tables, other recursion (a shallow copy of the descriptor)."""
+        if backend not in BACKENDS:
+            raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
+        other = object.__new__(DeviceProblem)
+        other.__dict__.update(self.__dict__)
+        other.desc = nat.Problem.from_buffer_copy(self.desc)
+        other.desc.backend = BACKENDS[backend]
+        return other
+
     @property
     def n_points(self):
         return self.plan.n_points
@@ -122,8 +132,12 @@ class DeviceOutputs:
         return total
 
 
-def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None):
-    """Launch the fused kernel for points ``[n_begin, n_end)`` into ``out`` (asynchronous)."""
+def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None, select="all"):
+    """Launch the fused kernel for points ``[n_begin, n_end)`` into ``out`` (asynchronous).
+
+    ``select``: "all" fills every buffer ``out`` holds; "power" only the power planes,
+    "no-power" everything else (used to take the power bookkeeping from the stable recursion
+    while r_ij / t_ij keep transfer-matrix semantics)."""
     n_end = problem.n_points if n_end is None else n_end
     if n_end - n_begin > out.n:
         raise ValueError("output buffers are smaller than the requested point range")
@@ -131,16 +145,17 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
     lib = nat.lib()
     if out.dtype == torch.complex128:
         o = nat.Outputs()
-        o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
-        o.mueller = out.mueller.data_ptr() if out.mueller is not None else None
-        o.stokes = out.stokes.data_ptr() if out.stokes is not None else None
-        if out.incident_stokes is not None:
-            o.incident_stokes = (C.c_double * 4)(*[float(x) for x in out.incident_stokes])
-        if out.power is not None:
+        if select != "power":
+            o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
+            o.mueller = out.mueller.data_ptr() if out.mueller is not None else None
+            o.stokes = out.stokes.data_ptr() if out.stokes is not None else None
+            if out.incident_stokes is not None:
+                o.incident_stokes = (C.c_double * 4)(*[float(x) for x in out.incident_stokes])
+        if out.power is not None and select != "no-power":
             if out.power.shape[0] != 2 * (len(problem.plan.layers) + 1):
                 raise ValueError("power buffer must have 2 * (n_layers + 1) planes")
             o.power, o.power_stride = out.power.data_ptr(), out.power.shape[1]
-        if out.t is not None:
+        if out.t is not None and select != "power":
             o.t_pp, o.t_ps, o.t_sp, o.t_ss = (out.t[i].data_ptr() for i in range(4))
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:

@@ -157,6 +157,19 @@ class Structure:
         plan = self.plan
         prob = engine.DeviceProblem(plan, backend, self.device)
         self.h2d_bytes = prob.h2d_bytes
+        # R, T, A_i are backend-independent physics; they always come from the stable recursion,
+        # which stays accurate where the transfer product is ill conditioned (two forward modes of a
+        # film growing at very different rates) or overflows.  r_ij, t_ij keep the requested semantics.
+        split_power = self.with_power and backend == "transfer"
+        prob_power = prob.with_backend("scattering") if split_power else None
+
+        def launch(buf, lo, hi, stream=None):
+            if split_power:
+                engine.reflect(prob, buf, lo, hi, stream=stream, select="no-power")
+                engine.reflect(prob_power, buf, lo, hi, stream=stream, select="power")
+            else:
+                engine.reflect(prob, buf, lo, hi, stream=stream)
+
         # multi-GPU: this process owns a contiguous slab of the slowest swept axis (no exchange step)
         base, n, shape = 0, plan.n_points, plan.fabt_shape
         if self.shard is not None:
@@ -171,7 +184,7 @@ class Structure:
         if self.keep_on_device:
             out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
                                        transmission=self.with_transmission)
-            engine.reflect(prob, out, base, base + n)
+            launch(out, base, base + n)
             r = out.r.reshape((4,) + shape)
             self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False)
             self.d2h_bytes = 0
@@ -194,7 +207,7 @@ class Structure:
             buf = bufs[ci % len(bufs)]
             if done[ci % len(bufs)] is not None:
                 compute.wait_event(done[ci % len(bufs)])  # previous D2H out of this buffer finished
-            engine.reflect(prob, buf, base + start, base + stop, stream=compute)
+            launch(buf, base + start, base + stop, stream=compute)
             ready = torch.cuda.Event()
             ready.record(compute)
             copy.wait_event(ready)

@@ -228,8 +228,9 @@ def test_power_bookkeeping(name, backend, built_library):
     s = _run_gpu(name, backend, with_power=True)
     fp = FieldProfile(s)
     mask = parity.transfer_mask(fx)
-    # the 11-layer stack under the transfer backend inherits the transfer product's noise
-    tol = 1e-5 if (name.startswith("c5") and backend == "transfer") else 1e-10
+    # (the drop-in takes R, T, A_i from the stable recursion under either backend; the fixtures are
+    # the reference's transfer + FieldProfile values, themselves ~1e-10 noisy on the 11-layer stack)
+    tol = 1e-9 if name.startswith("c5") else 1e-10
     for pol in "ps":
         summ = fp.summary(pol)
         got = {f"R_{pol}": summ["R"], f"T_{pol}": summ["T"]}
