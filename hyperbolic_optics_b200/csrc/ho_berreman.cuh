@@ -395,6 +395,16 @@ template <typename T> __device__ __forceinline__ void rank1_clean(Vec4<T>& r0, V
   r1 = sel(first, wc, v);
 }
 
+// rank-one structure of [r0 r1]: the larger column v and beta with  other column = beta v
+template <typename T> __device__ __forceinline__ void rank1_coeff(const Vec4<T>& r0, const Vec4<T>& r1, bool& first, cx<T>& beta) {
+  T n0 = norm2(r0), n1 = norm2(r1);
+  first = n0 >= n1;
+  cx<T> d = dotc(r0, r1);      // r0^H r1
+  if (!first) d = conj(d);     // r1^H r0
+  T nv = first ? n0 : n1;
+  beta = (nv > T(0)) ? ho_rcp(nv) * d : mk<T>(T(0), T(0));
+}
+
 // exp(c D) applied to two columns lying in one invariant subspace, given the pair's modes
 template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> lam_s, cx<T> phi_s, cx<T> dd, bool separated,
                                                                      const Vec4<T>& z0, const Vec4<T>& z1,
@@ -446,7 +456,7 @@ template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const
 // no projected intermediates.  Mixing all four exponentials in one polynomial costs log10 of their
 // ratio in digits (<= 2.6 here); thick films -- where that form loses the sub-dominant growing
 // mode, SURVEY 7.0-6a -- keep the invariant-subspace block form.
-template <typename T, bool NM> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1) {
+template <typename T, bool NM> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   cx<T> lf, phf, ddf, lb, phb, ddb;
@@ -454,6 +464,7 @@ template <typename T, bool NM> __device__ __forceinline__ void film_transfer(con
   T gf, gb;
   pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
   pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
+  w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
   if (thin_film(gf, gb)) {
     cx<T> a0, a1, a2, a3;
     cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
@@ -465,11 +476,32 @@ template <typename T, bool NM> __device__ __forceinline__ void film_transfer(con
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy0);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy1);
   Vec4<T> dzf0 = matvec(D, zf0), dzf1 = matvec(D, zf1);
-  Vec4<T> f0, f1, b0, b1;
-  block_exp_apply(lf, phf, ddf, sepf, zf0, zf1, dzf0, dzf1, f0, f1);
+  Vec4<T> b0, b1;
   block_exp_apply(lb, phb, ddb, sepb, sub(y0, zf0), sub(y1, zf1), sub(dy0, dzf0), sub(dy1, dzf1), b0, b1);
-  y0 = add(f0, b0);
-  y1 = add(f1, b1);
+  Vec4<T> r0 = axpy(-lf, zf0, dzf0), r1 = axpy(-lf, zf1, dzf1);
+  if (!sepf) {
+    y0 = add(axpy(ddf, r0, scale(phf, zf0)), b0);
+    y1 = add(axpy(ddf, r1, scale(phf, zf1)), b1);
+    return;
+  }
+  // The two forward modes grow at different rates: [r0 r1] is rank one (a multiple of the faster
+  // eigenvector), r_other = beta r_dom.  Adding phi_s z_k to the huge dd r_k would drown the
+  // slower mode in rounding error (ratio eps phi_g / phi_s), so the plane is re-based by the
+  // column operation  other <- other - beta dom, whose dominant parts cancel analytically:
+  //   dom   = phi_s z_dom + dd r_dom + b_dom,     other = phi_s (z_oth - beta z_dom) + (b_oth - beta b_dom).
+  // Same plane (r_ij unchanged), and w records the operation for the coordinate walk (t_ij, power).
+  bool first;
+  cx<T> beta;
+  rank1_coeff(r0, r1, first, beta);
+  if (first) {
+    y0 = add(axpy(ddf, r0, scale(phf, zf0)), b0);
+    y1 = add(scale(phf, axpy(-beta, zf0, zf1)), axpy(-beta, b0, b1));
+    w[1] = -beta;
+  } else {
+    y1 = add(axpy(ddf, r1, scale(phf, zf1)), b1);
+    y0 = add(scale(phf, axpy(-beta, zf1, zf0)), axpy(-beta, b1, b0));
+    w[2] = -beta;
+  }
 }
 
 // 2x2 inverse of [[m00, m01], [m10, m11]]
@@ -579,6 +611,7 @@ template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, c
     }
     y0 = axpy(B, dy0, scale(A, y0));
     y1 = axpy(B, dy1, scale(A, y1));
+    w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
     return;
   }
   // stable: forward branch of kz by the reference's mode rule (waves.py:273-289)

@@ -122,7 +122,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       const cx<T> c = mk<T>(T(0), -(k0 * d));
       if (STABLE) film_stable(D, s, c, y0, y1, w);
-      else film_transfer(D, s, c, y0, y1);
+      else film_transfer(D, s, c, y0, y1, w);
     }
   }
 }
@@ -152,7 +152,7 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
     if (want_power) st_stream(dst, T(1) - prev * inv_sinc);
 #pragma unroll 1
     for (int l = 1; l < P.n_layers; ++l) {
-      if (STABLE && l <= n_upper) {  // through film l-1 (an upper layer, per-point map)
+      if (l <= n_upper) {  // through film l-1 (an upper layer, per-point map; identity for most transfer films)
         cx<T> b0 = fma(wm[l - 1][1], a1, wm[l - 1][0] * a0);
         a1 = fma(wm[l - 1][3], a1, wm[l - 1][2] * a0);
         a0 = b0;
@@ -245,7 +245,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     // POWER only (dead otherwise): flux form at the top of every layer and, for the stable
     // recursion, the coordinate map through every film
     T hf[POWER ? HO_MAX_LAYERS : 1][4];
-    cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
+    cx<T> wm[POWER ? HO_MAX_LAYERS : 1][4];
     cx<T> binv[4];
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
@@ -253,7 +253,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
       apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv);
       if constexpr (POWER) {
         flux_form(y0, y1, hf[l]);
-        if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
+        wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];
       }
     }
     emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, P.n_layers, nullptr, binv);
@@ -315,7 +315,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
         const T k = __ldg(P.kx + a), k0 = __ldg(P.k0 + f);
         Vec4<T> y0, y1;
         T hf[POWER ? HO_MAX_LAYERS : 1][4];
-        cx<T> wm[(POWER && STABLE) ? HO_MAX_LAYERS : 1][4];
+        cx<T> wm[POWER ? HO_MAX_LAYERS : 1][4];
         cx<T> binv[4];
         int l_hi = P.n_layers - 1, l_lo = swept + 1;
         if (pass > 0) {
@@ -329,7 +329,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
           apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv);
           if constexpr (POWER) {
             flux_form(y0, y1, hf[l]);
-            if constexpr (STABLE) { wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3]; }
+            wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];
           }
         }
         if (pass == 0) {
@@ -351,7 +351,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
               cx<T> x = (2.0 * h0) * cmulc(m01, m00) + (2.0 * h1) * cmulc(m11, m10) + cmulc(m11, m00) * h01
                         + cmulc(m01, m10) * conj(h01);
               dst[2] = x.re; dst[3] = x.im;
-              if constexpr (STABLE) {
+              {
                 if (l < P.n_layers - 1) {  // M <- W_l M
                   cx<T> a00 = fma(wm[l][1], m10, wm[l][0] * m00), a01 = fma(wm[l][1], m11, wm[l][0] * m01);
                   cx<T> a10 = fma(wm[l][3], m10, wm[l][2] * m00), a11 = fma(wm[l][3], m11, wm[l][2] * m01);

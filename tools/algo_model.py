@@ -411,22 +411,50 @@ def block_exp_apply(D, Z, s, p, cfac, clean=True):
 MONO_GROWTH = 3.0  # thin-film switch: all four |Re(cfac lambda)| below this -> one cubic polynomial
 
 
-def film_transfer(D, Y, spec, cfac, clean=True, mono=True):
-    """exp(cfac D) Y: invariant-subspace block form, or (thin films) the monolithic cubic."""
+def film_transfer(D, Y, spec, cfac, clean=True, mono=True, return_w=False):
+    """exp(cfac D) Y.  Thin films: the monolithic cubic.  Otherwise the invariant-subspace block
+    form; when the two forward modes grow at different rates ("separated") the plane is re-based by
+    the column operation  other <- other - beta dom  (r_other = beta r_dom, rank one), whose dominant
+    parts cancel analytically -- adding phi_s z to the huge dd r would drown the slower mode."""
     sf, pf, sb, pb = spec
     zf, zb = [], []
     for y in Y:
         z, _ = project_forward(D, y, sf, pf, sb, pb)
         zf.append(z)
         zb.append(tuple(y[i] - z[i] for i in range(4)))
-    gf = block_exp_apply(D, zf, sf, pf, cfac, clean)
+    lam_s, phi_s, dd, sep = pair_modes(sf, pf, cfac)
+    R = []
+    for z in zf:
+        dz = matvec(D, z)
+        R.append(tuple(dz[i] - lam_s * z[i] for i in range(4)))
     gb = block_exp_apply(D, zb, sb, pb, cfac, clean)
-    block = [tuple(gf[k][i] + gb[k][i] for i in range(4)) for k in range(2)]
-    if not mono:
+    plain = [tuple(phi_s * zf[k][i] + dd * R[k][i] + gb[k][i] for i in range(4)) for k in range(2)]
+    n0 = sum(np.abs(R[0][i]) ** 2 for i in range(4))
+    n1 = sum(np.abs(R[1][i]) ** 2 for i in range(4))
+    first = n0 >= n1
+    pick = lambda a, b: [np.where(first, a[i], b[i]) for i in range(4)]
+    v, w = pick(R[0], R[1]), pick(R[1], R[0])
+    nv = np.where(first, n0, n1)
+    beta = sum(np.conj(v[i]) * w[i] for i in range(4)) / np.where(nv > 0, nv, 1.0)
+    zv, zw = pick(zf[0], zf[1]), pick(zf[1], zf[0])
+    bv, bw = pick(gb[0], gb[1]), pick(gb[1], gb[0])
+    dom = [phi_s * zv[i] + dd * v[i] + bv[i] for i in range(4)]
+    oth = [phi_s * (zw[i] - beta * zv[i]) + (bw[i] - beta * bv[i]) for i in range(4)]
+    rebased = [tuple(np.where(first, dom[i], oth[i]) for i in range(4)),
+               tuple(np.where(first, oth[i], dom[i]) for i in range(4))]
+    block = [tuple(np.where(sep, rebased[k][i], plain[k][i]) for i in range(4)) for k in range(2)]
+    thin = (film_growth(spec, cfac) < MONO_GROWTH) if mono else np.zeros(np.shape(sep), dtype=bool)
+    if mono:
+        poly = film_transfer_mono(D, Y, spec, cfac)
+        block = [tuple(np.where(thin, poly[k][i], block[k][i]) for i in range(4)) for k in range(2)]
+    if not return_w:
         return block
-    thin = film_growth(spec, cfac) < MONO_GROWTH
-    poly = film_transfer_mono(D, Y, spec, cfac)
-    return [tuple(np.where(thin, poly[k][i], block[k][i]) for i in range(4)) for k in range(2)]
+    # coordinate map of the column operation (identity unless re-based): c_bottom = W c_top
+    used = sep & ~thin
+    one, zero = np.ones_like(beta), np.zeros_like(beta)
+    w01 = np.where(used & first, -beta, zero)
+    w10 = np.where(used & ~first, -beta, zero)
+    return block, ((one, w01), (w10, one))
 
 
 def _inv2(m00, m01, m10, m11):

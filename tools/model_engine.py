@@ -73,8 +73,7 @@ def run(plan, backend="transfer", stats=None, **kw):
                 if stable:
                     Y, w = am.film_stable(D, Y, spec[:4], cfac, return_w=True)
                 else:
-                    w = None
-                    Y = am.film_transfer(D, Y, spec[:4], cfac)
+                    Y, w = am.film_transfer(D, Y, spec[:4], cfac, return_w=True)
             forms.append(am.flux_form(Y)); maps.append(w)
         r_pp, r_ps, r_sp, r_ss = am.reflect_from_plane(
             Y, plan.prism_inv_cos[a], plan.prism_inv_ncos[a], plan.prism_inv_n)
