@@ -130,27 +130,30 @@ def test_random_stacks_match_oracle(block, built_library):
         assert fin.mean() > 0.9, f"seed {seed}"
         assert err[fin].max() <= 1e-9, f"seed {seed} scattering: {err[fin].max():.3e}\n{entry['payload']}"
         worst_s = max(worst_s, float(err[fin].max()))
-        # transfer backend: on the reference's trust region (its two backends agree, cond < 1e10)
+        # transfer backend: no trust region -- wherever it is finite it must agree with the
+        # reference's *stable* result (the reference's own transfer product does not, on thick films)
         t = _gpu(entry, "transfer")
         got_t = {k: getattr(t, k) for k in parity.R_KEYS}
-        err_t = parity.jones_error(got_t, ref_t)
+        err_t = parity.jones_error(got_t, ref_s)
+        mask = np.isfinite(err_t)
+        if mask.any():
+            assert err_t[mask].max() <= 1e-9, f"seed {seed} transfer: {err_t[mask].max():.3e}\n{entry['payload']}"
+            worst_t = max(worst_t, float(err_t[mask].max()))
+        # power bookkeeping vs the reference's transfer + FieldProfile walk, where that walk is sound
         g = ref_t["transfer_matrix"]
         blk = np.stack([np.stack([g[..., 0, 0], g[..., 0, 2]], -1), np.stack([g[..., 2, 0], g[..., 2, 2]], -1)], -2)
         finb = np.isfinite(blk).all(axis=(-1, -2))
         cond = np.full(finb.shape, np.inf)
         cond[finb] = np.linalg.cond(blk[finb])
-        mask = np.isfinite(err_t) & (oracle.present(cond) < 1e10) & (parity.jones_error(ref_t, ref_s) <= 1e-11)
-        if mask.any():
-            assert err_t[mask].max() <= 1e-9, f"seed {seed} transfer: {err_t[mask].max():.3e}\n{entry['payload']}"
-            worst_t = max(worst_t, float(err_t[mask].max()))
-            # power bookkeeping of the stable recursion vs the reference's transfer + FieldProfile walk
+        sound = (oracle.present(cond) < 1e10) & (parity.jones_error(ref_t, ref_s) <= 1e-11)
+        if sound.any():
             for pol in "ps":
-                d = np.abs(np.asarray(s.power[pol]["R"]) - ref_t[f"R_{pol}"])[mask]
+                d = np.abs(np.asarray(s.power[pol]["R"]) - ref_t[f"R_{pol}"])[sound]
                 assert d.max() <= 1e-8, f"seed {seed} R_{pol}: {d.max():.3e}"
         n_points += err.size
         n_trusted += int(mask.sum())
     print(f"block {block}: {n_points} points, worst Jones rel err scattering {worst_s:.2e}, "
-          f"transfer {worst_t:.2e} on {n_trusted} trusted points")
+          f"transfer (unmasked) {worst_t:.2e} on {n_trusted} finite points")
 
 
 def extreme_case(seed):
