@@ -14,6 +14,7 @@ error: the transfer backend returns inf/NaN where the reference's 4x4 product ov
 
 Additions (all optional): ``shard=(rank, world_size)`` (one process per GPU: this process
 computes -- and returns -- only its contiguous slab of the slowest swept axis, ``sharding.py``),
+``precision="complex64"`` (opt-in single-precision kernels, 1e-4; r_ij + Mueller only),
 ``mueller`` (the sample Mueller matrix, fused into the same kernel), ``stokes`` for a given incident Stokes vector, ``power=True`` (R, T and layer-resolved
 absorption for p and s incidence from the same launch, both backends; consumed by
 ``hyperbolic_optics_b200.FieldProfile``), ``device=`` / ``keep_on_device=``.
@@ -78,6 +79,7 @@ class Structure:
         self.own_results = True
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.precision = "complex128"
         self.shard = None          # (rank, world_size) or None
         self.point_range = None    # [n_begin, n_end) of the presentation-ordered grid this run computed
         self._backend = "transfer"
@@ -131,7 +133,8 @@ class Structure:
 
     # -- one-call protocol ---------------------------------------------------------------
     def execute(self, payload, backend="transfer", mueller=True, incident_stokes=None,
-                keep_on_device=False, own_results=None, power=False, transmission=False, shard=None):
+                keep_on_device=False, own_results=None, power=False, transmission=False, shard=None,
+                precision="complex128"):
         if backend not in ("transfer", "scattering"):
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
         self.with_mueller = bool(mueller)
@@ -141,6 +144,11 @@ class Structure:
         self.keep_on_device = bool(keep_on_device)
         if own_results is not None:
             self.own_results = bool(own_results)
+        if precision not in ("complex128", "complex64"):
+            raise ValueError(f"Unknown precision {precision!r}; use 'complex128' or 'complex64'.")
+        if precision == "complex64" and (power or transmission or incident_stokes is not None):
+            raise ValueError("the complex64 kernels produce r_ij and the Mueller matrix only")
+        self.precision = precision
         if shard is not None:
             rank, world = (int(x) for x in shard)
             if not 0 <= rank < world:
@@ -181,9 +189,11 @@ class Structure:
             raise ValueError(f"shard {self.shard}: more ranks than samples of the sharded axis")
         want_stokes = self.incident_stokes is not None
         planes = 2 * (len(plan.layers) + 1) if self.with_power else 0
+        cdtype = torch.complex64 if self.precision == "complex64" else torch.complex128
+        rdtype = torch.float32 if self.precision == "complex64" else torch.float64
         if self.keep_on_device:
             out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
-                                       transmission=self.with_transmission)
+                                       transmission=self.with_transmission, dtype=cdtype)
             launch(out, base, base + n)
             r = out.r.reshape((4,) + shape)
             self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False)
@@ -191,13 +201,13 @@ class Structure:
             return
         # host results: kernel -> device chunk (double buffered) -> pinned host, D2H on a copy stream
         chunk = min(n, self.chunk_points)
-        host_r = _pinned("r", (4, n), torch.complex128)
-        host_m = _pinned("m", (n, 4, 4), torch.float64) if self.with_mueller else None
+        host_r = _pinned("r", (4, n), cdtype)
+        host_m = _pinned("m", (n, 4, 4), rdtype) if self.with_mueller else None
         host_s = _pinned("s", (n, 4), torch.float64) if want_stokes else None
         host_p = _pinned("p", (planes, n), torch.float64) if planes else None
         host_t = _pinned("t", (4, n), torch.complex128) if self.with_transmission else None
         bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
-                                     transmission=self.with_transmission)
+                                     transmission=self.with_transmission, dtype=cdtype)
                 for _ in range(2 if n > chunk else 1)]
         compute = torch.cuda.current_stream(prob.device)
         copy = torch.cuda.Stream(prob.device)
@@ -228,8 +238,9 @@ class Structure:
                 ev.record(copy)
             done[ci % len(bufs)] = ev
         copy.synchronize()
-        self.d2h_bytes = n * (64 + (128 if host_m is not None else 0) + (32 if host_s is not None else 0) + 8 * planes
-                              + (64 if host_t is not None else 0))
+        scale = 2 if self.precision == "complex128" else 1
+        self.d2h_bytes = n * ((32 + (64 if host_m is not None else 0)) * scale
+                              + (32 if host_s is not None else 0) + 8 * planes + (64 if host_t is not None else 0))
         self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, host_t, shape, to_numpy=True)
 
     def _assign(self, r, mueller, stokes, power, trans, shape, to_numpy):
