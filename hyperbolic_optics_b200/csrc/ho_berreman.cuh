@@ -306,37 +306,49 @@ template <typename T> __device__ __forceinline__ cx<T> forward_sqrt(cx<T> y) {
 // tensors up to the reference's hidden 1e-8 angle offsets -- every un-tilted crystal) the quartic
 // is a perturbed biquadratic and the forward pair comes from three square roots; otherwise
 // Ferrari + classification.  A biquadratic start that fails to converge falls back to Ferrari.
-template <typename T, bool NM> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D) {
+// FAST (fast-path kernel): only the biquadratic start is compiled; a point that would need
+// Ferrari sets `bail` and is finished later by the general kernel.
+template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D, bool& bail) {
   cx<T> c3, c2, c1, c0;
   charpoly(D, c3, c2, c1, c0);
   const T tau4 = T(1e-20);
   T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
   bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
   cx<T> u, v, b1, b0;
-#pragma unroll 1
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if (biq) {
-      cx<T> y0, y1;
-      quad_roots(c2, c0, y0, y1);
-      cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
-      u = -(m0 + m1);
-      v = m0 * m1;
-    } else {
-      cx<T> lam[4];
-      start_roots(c3, c2, c1, c0, lam);
-      bool fwd[4];
-      classify(lam, fwd);
-      cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
-      }
-      u = -sf;
-      v = pf;
-    }
+  if constexpr (FAST) {
+    cx<T> y0, y1;
+    quad_roots(c2, c0, y0, y1);
+    cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
+    u = -(m0 + m1);
+    v = m0 * m1;
     bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
-    if (ok || !biq) break;
-    biq = false;
+    bail = bail || !biq || !ok;
+  } else {
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (biq) {
+        cx<T> y0, y1;
+        quad_roots(c2, c0, y0, y1);
+        cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
+        u = -(m0 + m1);
+        v = m0 * m1;
+      } else {
+        cx<T> lam[4];
+        start_roots(c3, c2, c1, c0, lam);
+        bool fwd[4];
+        classify(lam, fwd);
+        cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (fwd[i]) { sf = sf + lam[i]; pf = pf * lam[i]; }
+        }
+        u = -sf;
+        v = pf;
+      }
+      bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
+      if (ok || !biq) break;
+      biq = false;
+    }
   }
   Spectrum<T> s;
   s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
@@ -456,7 +468,7 @@ template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const
 // no projected intermediates.  Mixing all four exponentials in one polynomial costs log10 of their
 // ratio in digits (<= 2.6 here); thick films -- where that form loses the sub-dominant growing
 // mode, SURVEY 7.0-6a -- keep the invariant-subspace block form.
-template <typename T, bool NM> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
+template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   cx<T> lf, phf, ddf, lb, phb, ddb;
@@ -472,6 +484,7 @@ template <typename T, bool NM> __device__ __forceinline__ void film_transfer(con
     cubic_apply(D, a0, a1, a2, a3, y1);
     return;
   }
+  if constexpr (FAST) { bail = true; return; }  // thick film: left to the general kernel
   Vec4<T> dy0, dy1;
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy0);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy1);
@@ -519,7 +532,7 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 // Renormalises so that rows (Ex, Ey) of the forward part are the identity.
 // w[0..3] = (w00, w01, w10, w11): the 2x2 map W with Y_new = exp(cD) Y_old W, i.e. coordinates at
 // the top of the film -> coordinates at its bottom (used by the power bookkeeping only).
-template <typename T, bool NM> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
+template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   // Thin film (all four |Re(c lambda)| < 3): nothing can overflow and the four exponentials are
@@ -543,6 +556,7 @@ template <typename T, bool NM> __device__ __forceinline__ void film_stable(const
     y0 = t0;
     return;
   }
+  if constexpr (FAST) { bail = true; return; }  // thick film: left to the general kernel
   Vec4<T> dy;
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy);

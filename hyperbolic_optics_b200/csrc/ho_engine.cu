@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "ho_b200.h"
 #include "ho_berreman.cuh"
@@ -86,9 +88,12 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
 // the stable recursion (power bookkeeping only; dead code otherwise).
 // binv (EXTRAS): kernel exit basis -> the reference's exit-mode amplitudes (transmission coefficients).
-template <typename T, bool STABLE, bool NM, bool EXTRAS>
+// FAST: fast-path build of the layer code (biquadratic start, thin-film cubic only); sets `bail`
+// when the point needs the general paths.
+template <typename T, bool STABLE, bool NM, bool EXTRAS, bool FAST = false>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
-                                            ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4]) {
+                                            ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4],
+                                            bool& bail) {
   using namespace ho;
   // isotropic crystal (scalar eps(f), mu(f), e.g. SiC): closed-form modes, no quartic
   const bool iso_crystal = (L.kind == HO_ANISO_FILM || L.kind == HO_ANISO_EXIT) && L.eps_scalar && L.mu_scalar;
@@ -114,15 +119,15 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     // crystal film or crystal exit: one instance of the Delta assembly + spectral split
     ZRow<T> z;
     Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
-    Spectrum<T> s = split_spectrum(D);
+    Spectrum<T> s = split_spectrum<T, NM, FAST>(D, bail);
     if (L.kind == HO_ANISO_EXIT) {
       substrate_plane(D, s, y0, y1);
       if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
     } else {
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       const cx<T> c = mk<T>(T(0), -(k0 * d));
-      if (STABLE) film_stable(D, s, c, y0, y1, w);
-      else film_transfer(D, s, c, y0, y1, w);
+      if (STABLE) film_stable<T, NM, FAST>(D, s, c, y0, y1, w, bail);
+      else film_transfer<T, NM, FAST>(D, s, c, y0, y1, w, bail);
     }
   }
 }
@@ -213,16 +218,43 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
   }
 }
 
+// Fast-path / fix-up protocol (two launches on the same stream, no host round trip):
+//   1. the FAST build of the kernel -- only the biquadratic start and the thin-film cubic are
+//      compiled in: 162 registers without spills and 40 % less code than the general build --
+//      evaluates every point it can and stores a sentinel NaN in r_pp where it cannot;
+//   2. the general build runs in fix-up mode: it only evaluates sentinel points.  A byte per tile of
+//      128 points (stream-ordered scratch, set by the fast launch) lets it skip clean tiles without
+//      touching r_pp, so a sweep with no or few deferred points pays microseconds, not a 1.6 GB scan.
+// The host only picks this when the plan says every crystal is un-tilted (hint_fast_path), so on
+// sweeps where the fast path applies nowhere the first launch is not wasted.
+constexpr unsigned long long kSentinelBits = 0x7ff8b200f00dcafeULL;  // a quiet NaN no arithmetic produces
+
+template <typename T> __device__ __forceinline__ bool is_sentinel(const ho::cx<T>* p);
+template <> __device__ __forceinline__ bool is_sentinel<double>(const ho::cx<double>* p) {
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  return (unsigned long long)__double_as_longlong(v.x) == kSentinelBits && (unsigned long long)__double_as_longlong(v.y) == kSentinelBits;
+}
+template <> __device__ __forceinline__ bool is_sentinel<float>(const ho::cx<float>*) { return false; }
+
+enum { MODE_ALL = 0, MODE_FIXUP = 1 };
+constexpr int kTileShift = 7;  // 128 points per flag byte
+
 // NM: every crystal layer of the stack has mu proportional to the identity (all built-in
 // materials) -> sparser Berreman matrix; the general kernel handles full mu tensors.
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
-template <typename T, bool STABLE, bool NM, bool POWER>
+// FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only points whose r_pp holds the sentinel.
+template <typename T, bool STABLE, bool NM, bool POWER, bool FAST>
 __global__ void __launch_bounds__(kThreads, HO_MIN_BLOCKS)
-reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end) {
+reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
+               unsigned char* tile_flags) {
   using namespace ho;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool small = n_end <= (int64_t)0x7fffffff;
   for (int64_t n = n_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_end; n += stride) {
+    if (mode == MODE_FIXUP) {
+      if (tile_flags[(n - n_begin) >> kTileShift] == 0) continue;      // warp-uniform: clean tile
+      if (!is_sentinel<T>(out.r_pp + (n - n_begin))) continue;
+    }
     // n = ((f*A + a)*B + b)*T + t   (presentation order, reference axes.py:83-95)
     int t, b, a, f;
     if (small) {  // 32-bit index arithmetic when the grid allows it (64-bit div/mod is ~4x the work)
@@ -242,18 +274,30 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     const T k0 = T(__ldg(P.k0 + f));
 
     Vec4<T> y0, y1;
-    // POWER only (dead otherwise): flux form at the top of every layer and, for the stable
-    // recursion, the coordinate map through every film
+    // POWER only (dead otherwise): flux form at the top of every layer and the coordinate map
+    // through every film
     T hf[POWER ? HO_MAX_LAYERS : 1][4];
     cx<T> wm[POWER ? HO_MAX_LAYERS : 1][4];
     cx<T> binv[4];
+    bool bail = false;
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
       cx<T> w[4];
-      apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv);
+      apply_layer<T, STABLE, NM, POWER, FAST>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail);
+      if constexpr (FAST) {
+        if (bail) break;
+      }
       if constexpr (POWER) {
         flux_form(y0, y1, hf[l]);
         wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];
+      }
+    }
+    if constexpr (FAST) {
+      if (bail) {  // left to the fix-up launch
+        const double nan_mark = __longlong_as_double((long long)kSentinelBits);
+        st_stream(out.r_pp + (n - n_begin), mk<T>(T(nan_mark), T(nan_mark)));
+        tile_flags[(n - n_begin) >> kTileShift] = 1;  // plain store: every deferring thread of the tile writes 1
+        continue;
       }
     }
     emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, P.n_layers, nullptr, binv);
@@ -326,7 +370,8 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
 #pragma unroll 1
         for (int l = l_hi; l >= l_lo; --l) {
           cx<T> w[4];
-          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv);
+          bool bail = false;  // (general build: never set)
+          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail);
           if constexpr (POWER) {
             flux_form(y0, y1, hf[l]);
             wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];
@@ -428,6 +473,34 @@ int validate(const ho_problem_t* p, int64_t n_begin, int64_t n_end) {
   return HO_OK;
 }
 
+// Tile flags of the fast-path protocol: one library-owned buffer per (device, stream), grown on
+// demand and kept (n/128 bytes: 0.8 MB for 1e8 points).  Work on one stream is ordered, so the
+// buffer can be reused by the next launch on that stream without synchronisation.
+unsigned char* tile_scratch(size_t bytes, cudaStream_t stream) {
+  struct Slot { int dev; cudaStream_t stream; unsigned char* ptr; size_t cap; };
+  static std::mutex mu;
+  static std::vector<Slot> slots;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (Slot& s : slots) {
+    if (s.dev == dev && s.stream == stream) {
+      if (s.cap >= bytes) return s.ptr;
+      cudaStreamSynchronize(stream);  // the old buffer may still be in use by queued launches
+      cudaFree(s.ptr);
+      s.ptr = nullptr; s.cap = 0;
+      if (cudaMalloc((void**)&s.ptr, bytes + bytes / 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      s.cap = bytes + bytes / 2;
+      return s.ptr;
+    }
+  }
+  Slot s{dev, stream, nullptr, 0};
+  if (cudaMalloc((void**)&s.ptr, bytes + bytes / 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  s.cap = bytes + bytes / 2;
+  slots.push_back(s);
+  return s.ptr;
+}
+
 int grid_for(int64_t n, const void* kernel) {
   int dev = 0, sms = 148, per_sm = 4;
   cudaGetDevice(&dev);
@@ -487,8 +560,26 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
     if (p->T > 1 && swept >= 0 && !(env && atoi(env) == 0))
       return launch_tsweep<STABLE, NM, POWER>(p, out, n_begin, n_end, swept, stream);
   }
-  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER>;
-  reflect_kernel<T, STABLE, NM, POWER><<<grid_for(n_end - n_begin, kern), kThreads, 0, stream>>>(*p, out, n_begin, n_end);
+  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, false>;
+  const int grid = grid_for(n_end - n_begin, kern);
+  if constexpr (sizeof(T) == 8 && !POWER) {
+    const char* env = getenv("HO_B200_FAST_PATH");  // test hook: 0 disables, 1 forces the two-launch protocol
+    // (below ~4M points the second launch costs more than the leaner kernel saves)
+    const bool want = env ? atoi(env) != 0 : (p->hint_fast_path != 0 && n_end - n_begin >= (int64_t)1 << 22);
+    if (want && out.r_pp) {
+      const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, true>;
+      const size_t tiles = (size_t)((n_end - n_begin + (1 << kTileShift) - 1) >> kTileShift);
+      unsigned char* flags = tile_scratch(tiles, stream);
+      if (flags) {
+        cudaMemsetAsync(flags, 0, tiles, stream);
+        reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n_end - n_begin, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, flags);
+        reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, flags);
+        g_launches.fetch_add(1);
+        return 0;
+      }
+    }
+  }
+  reflect_kernel<T, STABLE, NM, POWER, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr);
   return 0;
 }
 

@@ -42,6 +42,7 @@ class DeviceProblem:
         d.A, d.B, d.F, d.T = plan.A, plan.B, plan.F, plan.T
         d.n_layers = len(plan.layers)
         d.backend = BACKENDS[backend]
+        d.hint_fast_path = 1 if plan.fast_path else 0
         d.prism_inv_n = plan.prism_inv_n
         slots = [("kx", self._put_f64(plan.kx)), ("k0", self._put_f64(plan.k0)),
                  ("prism_inv_cos", self._put_f64(plan.prism_inv_cos)),

@@ -77,6 +77,7 @@ class StackPlan:
     frequency: np.ndarray | None = None
     eps_prism: float | None = None
     k0_all: np.ndarray | None = None   # 2 pi f for every requested frequency (k0 may be collapsed to one entry)
+    fast_path: bool = False            # every crystal un-tilted: the fast-path kernel applies (performance hint)
 
     @property
     def n_points(self):
@@ -237,7 +238,18 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
     if not plan.layers or plan.layers[-1].kind not in (KIND_ANISO_EXIT, KIND_ISO_EXIT):
         raise ValueError("the stack must end with a semi-infinite exit layer")
     _collapse_unswept_axes(plan)
+    plan.fast_path = all(_untilted(lp) for lp in plan.layers if lp.kind in (KIND_ANISO_FILM, KIND_ANISO_EXIT))
     return plan
+
+
+def _untilted(lp) -> bool:
+    """z is a principal axis of the (Ry Rx)-rotated tensors, up to the reference's hidden 1e-8 offset:
+    then the characteristic quartic is a perturbed biquadratic at every point (any azimuth)."""
+    for table in (lp.eps, lp.mu):
+        diag = np.abs(table[:, [0, 3, 5]]).max()
+        if np.abs(table[:, [2, 4]]).max() > 1e-6 * max(diag, 1e-300):
+            return False
+    return True
 
 
 def _collapse_unswept_axes(plan: StackPlan) -> None:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 4
+#define HO_ABI_VERSION 5
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -80,6 +80,10 @@ typedef struct {
   int32_t A, B, F, T;            /* canonical batch sizes (axes.py:21) */
   int32_t n_layers;              /* layers below the prism, <= HO_MAX_LAYERS */
   int32_t backend;               /* ho_backend */
+  int32_t hint_fast_path;        /* 1: every crystal layer is un-tilted (z is a principal axis of its rotated
+                                    tensors up to the reference's 1e-8 offsets), so the fast-path kernel applies
+                                    to (almost) every point; a performance hint only -- points it cannot
+                                    evaluate are finished by the general kernel either way */
   const double* kx;              /* [A] sqrt(eps_prism) sin(theta)       structure.py:183 */
   const double* k0;              /* [F] 2 pi f                           structure.py:189 */
   const double* prism_inv_cos;   /* [A] 1/cos(theta)                     layers.py:109-152 */

@@ -642,3 +642,37 @@ def test_transfer_backend_unmasked_vs_stable_reference(name, built_library):
     assert fin.mean() > 0.95
     worst = float(np.nanmax(err[fin])) if np.ndim(err) else float(err)
     assert worst <= 1e-10, f"{name}: transfer vs stable reference, unmasked: {worst:.3e}"
+
+
+@pytest.mark.parametrize("name", ["c4_fullsweep_hbn_sic", "dispersion_calcite", "multilayer_incident", "c1_incident_calcite",
+                                  "gallium_oxide_incident", "magnetic_gap_incident", "dispersion_iso_exit"])
+def test_fast_path_protocol_equals_general_kernel(name, built_library, monkeypatch):
+    """Fast-path kernel + fix-up launch (sentinel protocol) vs the general kernel alone: same
+    results whether the fast path evaluates every point (un-tilted thin stacks), none (tilted
+    crystal: every point bails at the biquadratic test) or a part (thick film: bails per point)."""
+    from hyperbolic_optics_b200 import engine
+    from hyperbolic_optics_b200.plan import build_plan
+    from hyperbolic_optics_b200.scenario import ScenarioSetup
+
+    sc, payload = parity.scenario_for(name, ScenarioSetup)
+    plan = build_plan(sc, payload["Layers"])
+    n = plan.n_points
+    for backend in ("transfer", "scattering"):
+        prob = engine.DeviceProblem(plan, backend, "cuda:0")
+        res = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("HO_B200_FAST_PATH", flag)
+            out = engine.DeviceOutputs(n, prob.device)
+            before = engine.launch_count()
+            engine.reflect(prob, out)
+            torch.cuda.synchronize()
+            assert engine.launch_count() - before == (2 if flag == "1" else 1)
+            res[flag] = out
+        a, b = torch.view_as_real(res["1"].r), torch.view_as_real(res["0"].r)
+        fin = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), fin)
+        scale = b[fin].abs().max().item()
+        assert (a[fin] - b[fin]).abs().max().item() <= 1e-12 * max(scale, 1.0)
+        ma, mb = res["1"].mueller, res["0"].mueller
+        finm = torch.isfinite(mb)
+        assert (ma[finm] - mb[finm]).abs().max().item() <= 1e-12 * max(mb[finm].abs().max().item(), 1.0)
