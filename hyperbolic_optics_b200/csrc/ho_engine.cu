@@ -220,11 +220,12 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
 
 // Fast-path / fix-up protocol (two launches on the same stream, no host round trip):
 //   1. the FAST build of the kernel -- only the biquadratic start and the thin-film cubic are
-//      compiled in: 162 registers without spills and 40 % less code than the general build --
-//      evaluates every point it can and stores a sentinel NaN in r_pp where it cannot;
-//   2. the general build runs in fix-up mode: it only evaluates sentinel points.  A byte per tile of
-//      128 points (stream-ordered scratch, set by the fast launch) lets it skip clean tiles without
-//      touching r_pp, so a sweep with no or few deferred points pays microseconds, not a 1.6 GB scan.
+//      compiled in: 160 registers without spills and 40 % less code than the general build --
+//      evaluates every point it can; where it cannot it stores a sentinel NaN in r_pp and appends
+//      the point to a work list (warp-aggregated atomic on a counter in stream-ordered scratch);
+//   2. the general build runs in fix-up mode over the compacted list: full warps of deferred
+//      points, microseconds when there are few.  If the list overflowed (more than `cap` points:
+//      the hint was wrong) it scans r_pp for the sentinel instead.
 // The host only picks this when the plan says every crystal is un-tilted (hint_fast_path), so on
 // sweeps where the fast path applies nowhere the first launch is not wasted.
 constexpr unsigned long long kSentinelBits = 0x7ff8b200f00dcafeULL;  // a quiet NaN no arithmetic produces
@@ -237,24 +238,32 @@ template <> __device__ __forceinline__ bool is_sentinel<double>(const ho::cx<dou
 template <> __device__ __forceinline__ bool is_sentinel<float>(const ho::cx<float>*) { return false; }
 
 enum { MODE_ALL = 0, MODE_FIXUP = 1 };
-constexpr int kTileShift = 7;  // 128 points per flag byte
 
 // NM: every crystal layer of the stack has mu proportional to the identity (all built-in
 // materials) -> sparser Berreman matrix; the general kernel handles full mu tensors.
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
-// FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only points whose r_pp holds the sentinel.
+// FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only the deferred points.
+// work[0] = number of deferred points, work[1 .. cap] = their indices relative to n_begin.
 template <typename T, bool STABLE, bool NM, bool POWER, bool FAST>
 __global__ void __launch_bounds__(kThreads, HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
-               unsigned char* tile_flags) {
+               unsigned* work, unsigned cap) {
   using namespace ho;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool small = n_end <= (int64_t)0x7fffffff;
-  for (int64_t n = n_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_end; n += stride) {
+  int64_t total = n_end - n_begin;
+  bool listed = false;
+  if (mode == MODE_FIXUP) {
+    const unsigned deferred = work[0];
+    if (deferred <= cap) { total = deferred; listed = true; }
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t rel = i;
     if (mode == MODE_FIXUP) {
-      if (tile_flags[(n - n_begin) >> kTileShift] == 0) continue;      // warp-uniform: clean tile
-      if (!is_sentinel<T>(out.r_pp + (n - n_begin))) continue;
+      if (listed) rel = work[1 + i];
+      else if (!is_sentinel<T>(out.r_pp + i)) continue;
     }
+    const int64_t n = n_begin + rel;
     // n = ((f*A + a)*B + b)*T + t   (presentation order, reference axes.py:83-95)
     int t, b, a, f;
     if (small) {  // 32-bit index arithmetic when the grid allows it (64-bit div/mod is ~4x the work)
@@ -295,12 +304,17 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     if constexpr (FAST) {
       if (bail) {  // left to the fix-up launch
         const double nan_mark = __longlong_as_double((long long)kSentinelBits);
-        st_stream(out.r_pp + (n - n_begin), mk<T>(T(nan_mark), T(nan_mark)));
-        tile_flags[(n - n_begin) >> kTileShift] = 1;  // plain store: every deferring thread of the tile writes 1
+        st_stream(out.r_pp + rel, mk<T>(T(nan_mark), T(nan_mark)));
+        const unsigned peers = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        unsigned slot = 0;
+        if (lane == leader) slot = atomicAdd(work, (unsigned)__popc(peers));
+        slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+        if (slot < cap) work[1 + slot] = (unsigned)rel;
         continue;
       }
     }
-    emit_point<T, STABLE, POWER>(P, out, n - n_begin, a, y0, y1, hf, wm, P.n_layers, nullptr, binv);
+    emit_point<T, STABLE, POWER>(P, out, rel, a, y0, y1, hf, wm, P.n_layers, nullptr, binv);
   }
 }
 
@@ -473,10 +487,10 @@ int validate(const ho_problem_t* p, int64_t n_begin, int64_t n_end) {
   return HO_OK;
 }
 
-// Tile flags of the fast-path protocol: one library-owned buffer per (device, stream), grown on
-// demand and kept (n/128 bytes: 0.8 MB for 1e8 points).  Work on one stream is ordered, so the
+// Work list of the fast-path protocol: one library-owned buffer per (device, stream), grown on
+// demand and kept (n/2 bytes: 50 MB for 1e8 points).  Work on one stream is ordered, so the
 // buffer can be reused by the next launch on that stream without synchronisation.
-unsigned char* tile_scratch(size_t bytes, cudaStream_t stream) {
+unsigned char* work_scratch(size_t bytes, cudaStream_t stream) {
   struct Slot { int dev; cudaStream_t stream; unsigned char* ptr; size_t cap; };
   static std::mutex mu;
   static std::vector<Slot> slots;
@@ -566,20 +580,23 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
     const char* env = getenv("HO_B200_FAST_PATH");  // test hook: 0 disables, 1 forces the two-launch protocol
     // (below ~4M points the second launch costs more than the leaner kernel saves)
     const bool want = env ? atoi(env) != 0 : (p->hint_fast_path != 0 && n_end - n_begin >= (int64_t)1 << 22);
-    if (want && out.r_pp) {
+    if (want && out.r_pp && n_end - n_begin < ((int64_t)1 << 32)) {
       const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, true>;
-      const size_t tiles = (size_t)((n_end - n_begin + (1 << kTileShift) - 1) >> kTileShift);
-      unsigned char* flags = tile_scratch(tiles, stream);
-      if (flags) {
-        cudaMemsetAsync(flags, 0, tiles, stream);
-        reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n_end - n_begin, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, flags);
-        reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, flags);
+      // room for 1/8 of the points on the list; beyond that the fix-up pass scans for the sentinel
+      int64_t cap = (n_end - n_begin) / 8 + 1024;
+      if (const char* c = getenv("HO_B200_FIXUP_CAP")) cap = atoll(c);  // test hook (0 forces the scan)
+      if (cap > (int64_t)0x7fffffff) cap = 0x7fffffff;
+      unsigned* work = (unsigned*)work_scratch((size_t)(cap + 1) * sizeof(unsigned), stream);
+      if (work) {
+        cudaMemsetAsync(work, 0, sizeof(unsigned), stream);
+        reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n_end - n_begin, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, work, (unsigned)cap);
+        reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, work, (unsigned)cap);
         g_launches.fetch_add(1);
         return 0;
       }
     }
   }
-  reflect_kernel<T, STABLE, NM, POWER, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr);
+  reflect_kernel<T, STABLE, NM, POWER, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr, 0u);
   return 0;
 }
 
