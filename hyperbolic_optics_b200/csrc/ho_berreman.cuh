@@ -517,6 +517,79 @@ template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ voi
   }
 }
 
+// cosh(z) and sinh(z)/z; series below |z| = 0.25 (no cancellation in e^z - e^-z, no 0/0)
+template <typename T> __device__ __forceinline__ void cosh_sinhc(cx<T> z, cx<T>& ch, cx<T>& shc) {
+  cx<T> z2 = z * z;
+  if (norm2(z2) < T(0.00390625)) {
+    const cx<T> one = mk<T>(T(1), T(0));
+    ch = fma(T(0.5) * z2, fma(T(1.0 / 12.0) * z2, fma(T(1.0 / 30.0) * z2, fma(T(1.0 / 56.0) * z2, fma(T(1.0 / 90.0) * z2, fma(T(1.0 / 132.0) * z2, one, one), one), one), one), one), one);
+    shc = fma(T(1.0 / 6.0) * z2, fma(T(1.0 / 20.0) * z2, fma(T(1.0 / 42.0) * z2, fma(T(1.0 / 72.0) * z2, fma(T(1.0 / 110.0) * z2, fma(T(1.0 / 156.0) * z2, one, one), one), one), one), one), one);
+  } else {
+    cx<T> e = cexp(z), ei = recip(e);
+    ch = T(0.5) * (e + ei);
+    shc = (T(0.5) * (e - ei)) * recip(z);
+  }
+}
+
+// Film of an un-tilted crystal (z a principal axis up to the reference's hidden 1e-8 tilt, any
+// in-plane rotation): det(x I - D) is a biquadratic x^4 + c2 x^2 + c0 plus odd coefficients of
+// the order of the tilt, so the roots come in pairs delta_i +- mu_i with delta_i ~ tilt.
+//   1. start from the biquadratic limit, q_0 = x^2 - y0 (y0, y1 the roots of y^2 + c2 y + c0).
+//      The Bairstow Jacobian there is -(y0 - y1) I up to O(tilt), so the polish is the fixed-point
+//      step (u, v) += (r1, r0) / (y0 - y1): linear convergence at rate ~ tilt |mu| / |y0 - y1|,
+//      three steps, the last one checked.
+//   2. on each pair exp(c x) is interpolated by
+//        alpha_i(x) = e^{c delta_i} [cosh(c mu_i) + (x - delta_i) sinh(c mu_i) / mu_i],
+//      entire and even in mu_i: no forward/backward classification, one exponential per pair.
+//   3. the two interpolants are merged into one cubic by the projector formula of cubic_coeffs.
+// Returns false when the point has to take the general path: odd coefficients not small, y0 ~ y1
+// (the merge would lose more than 3 digits: near-normal incidence on a c-cut uniaxial film),
+// polish not converged, or thick film (a |Re(c mu)| >= 3).
+template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c,
+                                                                                cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+  const T odd_tol = sizeof(T) == 8 ? T(1e-12) : T(1e-6);
+  const T step_tol = sizeof(T) == 8 ? T(1e-20) : T(1e-9);
+  T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
+  bool ok = (n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2));
+  cx<T> y0, y1;
+  quad_roots(c2, c0, y0, y1);
+  cx<T> dy = y0 - y1;
+  ok = ok && norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1));
+  if (!ok) return false;
+  cx<T> idy = recip(dy);
+  cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    b1 = c3 - u;
+    b0 = c2 - v - u * b1;
+    du = (c1 - u * b0 - v * b1) * idy;
+    dv = (c0 - v * b0) * idy;
+    u = u + du;
+    v = v + dv;
+  }
+  b1 = c3 - u;
+  b0 = c2 - v - u * b1;
+  T nv = norm2(v);
+  T ndu = norm2(du);
+  if (!(norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv)) return false;  // |du|^2 <= tol |v|
+  Spectrum<T> s;
+  s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
+  // pair 0
+  cx<T> d0 = T(0.5) * s.sf, d1 = T(0.5) * s.sb;
+  cx<T> z0 = c * csqrt(d0 * d0 - s.pf), z1 = c * csqrt(d1 * d1 - s.pb);
+  cx<T> x0 = c * d0, x1 = c * d1;
+  if (!(thin_film(ho_abs(z0.re), ho_abs(z1.re)) && norm2(x0) < T(1e-10) && norm2(x1) < T(1e-10))) return false;
+  cx<T> A0, S0, A1, S1;
+  cosh_sinhc(z0, A0, S0);
+  cosh_sinhc(z1, A1, S1);
+  const cx<T> one = mk<T>(T(1), T(0));
+  cx<T> e0 = one + x0 + T(0.5) * (x0 * x0), e1 = one + x1 + T(0.5) * (x1 * x1);  // e^{c delta}, |c delta| < 1e-5
+  cx<T> h0, h1;
+  projector_coeffs(s, h0, h1);
+  cubic_coeffs(s, h0, h1, d0, e0 * A0, e0 * (c * S0), d1, e1 * A1, e1 * (c * S1), a0, a1, a2, a3);
+  return true;
+}
+
 // 2x2 inverse of [[m00, m01], [m10, m11]]
 template <typename T> __device__ __forceinline__ void inv2(cx<T> m00, cx<T> m01, cx<T> m10, cx<T> m11, cx<T>& n00, cx<T>& n01, cx<T>& n10, cx<T>& n11) {
   cx<T> idet = recip(m00 * m11 - m01 * m10);
@@ -579,6 +652,23 @@ template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ voi
   y1 = axpy(g1.v1, e1, axpy(g1.v0, e0, xf1));
   w[0] = fma(n01, g0.v1, n00 * g0.v0); w[1] = fma(n01, g1.v1, n00 * g1.v0);
   w[2] = fma(n11, g0.v1, n10 * g0.v0); w[3] = fma(n11, g1.v1, n10 * g1.v0);
+}
+
+// Fast-path film: the pair-symmetric form above, then (stable recursion) the same re-basing as film_stable
+template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_biquadratic(const Delta<T, NM>& D, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+  cx<T> c3, c2, c1, c0, a0, a1, a2, a3;
+  charpoly(D, c3, c2, c1, c0);
+  if (!pair_symmetric_film_coeffs(c3, c2, c1, c0, c, a0, a1, a2, a3)) { bail = true; return; }
+  cubic_apply(D, a0, a1, a2, a3, y0);
+  cubic_apply(D, a0, a1, a2, a3, y1);
+  if constexpr (STABLE) {
+    inv2(y0.v0, y1.v0, y0.v1, y1.v1, w[0], w[1], w[2], w[3]);
+    Vec4<T> t0 = axpy(w[2], y1, scale(w[0], y0));
+    y1 = axpy(w[3], y1, scale(w[1], y0));
+    y0 = t0;
+  } else {
+    w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
+  }
 }
 
 // Forward invariant subspace of a semi-infinite crystal: q_b(D) [e0 e1], q_b(x) = x^2 - s_b x + p_b.

@@ -119,6 +119,13 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     // crystal film or crystal exit: one instance of the Delta assembly + spectral split
     ZRow<T> z;
     Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
+    if constexpr (FAST) {
+      if (L.kind == HO_ANISO_FILM) {  // un-tilted crystal film: closed form, no spectral split
+        const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
+        film_biquadratic<T, NM, STABLE>(D, mk<T>(T(0), -(k0 * d)), y0, y1, w, bail);
+        return;
+      }
+    }
     Spectrum<T> s = split_spectrum<T, NM, FAST>(D, bail);
     if (L.kind == HO_ANISO_EXIT) {
       substrate_plane(D, s, y0, y1);
@@ -590,6 +597,7 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
       if (work) {
         cudaMemsetAsync(work, 0, sizeof(unsigned), stream);
         reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n_end - n_begin, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, work, (unsigned)cap);
+        if (env && atoi(env) == 2) return 0;  // test hook: leave the deferred points marked (r_pp = sentinel NaN)
         reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, work, (unsigned)cap);
         g_launches.fetch_add(1);
         return 0;

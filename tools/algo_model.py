@@ -692,3 +692,88 @@ def film_growth(spec, cfac):
         h = np.sqrt(m * m - p)
         g = np.maximum(g, np.maximum(np.abs((cfac * (m + h)).real), np.abs((cfac * (m - h)).real)))
     return g
+
+
+# ----------------------------------------------------------------------------- un-tilted crystals: pair-symmetric film
+PAIR_ODD = 1e-12        # |c3|^2 <= PAIR_ODD |c2|, |c1|^2 <= PAIR_ODD |c2|^3: odd coefficients are a small perturbation
+PAIR_SEPARATION = 1e-6  # |y0 - y1|^2 >= PAIR_SEPARATION (|y0|^2 + |y1|^2): the pair mixing loses <= 3 digits
+PAIR_STEP = 1e-20       # |last polish step|^2 relative: converged
+
+
+def _cosh_sinhc(z):
+    """cosh(z) and sinh(z)/z, series below |z| = 0.25."""
+    z = np.asarray(z, dtype=complex)
+    z2 = z * z
+    small = np.abs(z2) < 0.0625
+    zs = np.where(small, 1.0, z)
+    e = np.exp(zs)
+    ei = 1.0 / e
+    ch_big, sh_big = 0.5 * (e + ei), 0.5 * (e - ei) / zs
+    ch = 1 + z2 / 2 * (1 + z2 / 12 * (1 + z2 / 30 * (1 + z2 / 56 * (1 + z2 / 90 * (1 + z2 / 132)))))
+    sh = 1 + z2 / 6 * (1 + z2 / 20 * (1 + z2 / 42 * (1 + z2 / 72 * (1 + z2 / 110 * (1 + z2 / 156)))))
+    return np.where(small, ch, ch_big), np.where(small, sh, sh_big)
+
+
+def pair_symmetric_split(c3, c2, c1, c0, iters=3):
+    """Quartic with small odd coefficients (un-tilted crystal + the reference's hidden 1e-8 tilt):
+    factors (x^2 + u x + v)(x^2 + b1 x + b0) grouped as the +-mu pairs of the biquadratic limit,
+    u, b1 ~ tilt.  Start (0, -y0); the Bairstow Jacobian there is -(y0 - y1) I up to O(tilt), so
+    the polish is the fixed-point step (u, v) += (r1, r0) / (y0 - y1): linear convergence at rate
+    ~ tilt |mu| / |y0 - y1|, three steps."""
+    y0, y1 = _quad_roots(c2, c0)
+    dy = y0 - y1
+    idy = 1.0 / np.where(dy == 0, 1.0, dy)
+    u, v = np.zeros_like(y0), -y0
+    for _ in range(iters):
+        b1 = c3 - u
+        b0 = c2 - v - u * b1
+        du, dv = (c1 - u * b0 - v * b1) * idy, (c0 - v * b0) * idy
+        u, v = u + du, v + dv
+    b1 = c3 - u
+    b0 = c2 - v - u * b1
+    n2 = np.abs(c2) ** 2
+    ok = (np.abs(c3) ** 4 <= PAIR_ODD * n2) & (np.abs(c1) ** 4 <= PAIR_ODD * n2 ** 3)
+    ok &= np.abs(dy) ** 2 >= PAIR_SEPARATION * (np.abs(y0) ** 2 + np.abs(y1) ** 2)
+    ok &= np.abs(du) ** 2 * np.abs(v) + np.abs(dv) ** 2 <= PAIR_STEP * np.abs(v) ** 2
+    return u, v, b1, b0, ok
+
+
+def film_pair_symmetric(D, Y, cfac):
+    """exp(cfac D) Y for a film whose quartic is a slightly perturbed biquadratic.
+
+    Root pairs delta_i +- mu_i (delta_i ~ tilt): on each pair exp(c x) is interpolated by
+        alpha_i(x) = e^{c delta_i} [cosh(c mu_i) + (x - delta_i) sinh(c mu_i) / mu_i],
+    entire and even in mu_i: no forward/backward classification, one complex exponential per pair.
+    The two interpolants are merged into one cubic by the same projector formula as the general
+    thin-film path.  Returns (columns, ok)."""
+    c3, c2, c1, c0 = charpoly(D)
+    u, v, b1, b0, ok = pair_symmetric_split(c3, c2, c1, c0)
+    coef = []
+    for (uu, vv) in ((u, v), (b1, b0)):
+        delta = -0.5 * uu
+        mu = np.sqrt(delta * delta - vv)
+        z = cfac * mu
+        ok = ok & (np.abs(z.real) < MONO_GROWTH)
+        A, S = _cosh_sinhc(z)
+        x = cfac * delta
+        ok = ok & (np.abs(x) ** 2 < 1e-10)
+        ed = 1 + x * (1 + 0.5 * x)
+        coef.append((delta, ed * A, ed * cfac * S))
+    (d0, A0, B0), (d1, A1, B1) = coef
+    sf, pf, sb, pb = -u, v, -b1, b0
+    af0, af1 = A0 - B0 * d0, B0
+    ab0, ab1 = A1 - B1 * d1, B1
+    h0, h1 = projector_coeffs(sf, pf, sb, pb)
+    e0, e1 = af0 - ab0, af1 - ab1
+    g0, g1, g2 = e0 * h0, e0 * h1 + e1 * h0, e1 * h1
+    a3 = g1 - sb * g2 - g2 * c3
+    a2 = g0 - sb * g1 + pb * g2 - g2 * c2
+    a1 = -sb * g0 + pb * g1 - g2 * c1 + ab1
+    a0 = pb * g0 - g2 * c0 + ab0
+    out = []
+    for y in Y:
+        v1 = matvec(D, y)
+        v2 = matvec(D, v1)
+        v3 = matvec(D, v2)
+        out.append(tuple(a0 * y[i] + a1 * v1[i] + a2 * v2[i] + a3 * v3[i] for i in range(4)))
+    return out, ok
