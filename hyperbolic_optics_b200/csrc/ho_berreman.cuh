@@ -308,9 +308,7 @@ template <typename T> __device__ __forceinline__ cx<T> forward_sqrt(cx<T> y) {
 // Ferrari + classification.  A biquadratic start that fails to converge falls back to Ferrari.
 // FAST (fast-path kernel): only the biquadratic start is compiled; a point that would need
 // Ferrari sets `bail` and is finished later by the general kernel.
-template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ Spectrum<T> split_spectrum(const Delta<T, NM>& D, bool& bail) {
-  cx<T> c3, c2, c1, c0;
-  charpoly(D, c3, c2, c1, c0);
+template <typename T, bool FAST = false> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail) {
   const T tau4 = T(1e-20);
   T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
   bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
@@ -550,12 +548,11 @@ template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs
   const T odd_tol = sizeof(T) == 8 ? T(1e-12) : T(1e-6);
   const T step_tol = sizeof(T) == 8 ? T(1e-20) : T(1e-9);
   T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
-  bool ok = (n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2));
+  if (!((n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2)))) return false;
   cx<T> y0, y1;
   quad_roots(c2, c0, y0, y1);
   cx<T> dy = y0 - y1;
-  ok = ok && norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1));
-  if (!ok) return false;
+  if (!(norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1)))) return false;
   cx<T> idy = recip(dy);
   cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
 #pragma unroll
@@ -655,9 +652,8 @@ template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ voi
 }
 
 // Fast-path film: the pair-symmetric form above, then (stable recursion) the same re-basing as film_stable
-template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_biquadratic(const Delta<T, NM>& D, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
-  cx<T> c3, c2, c1, c0, a0, a1, a2, a3;
-  charpoly(D, c3, c2, c1, c0);
+template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_biquadratic(const Delta<T, NM>& D, cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+  cx<T> a0, a1, a2, a3;
   if (!pair_symmetric_film_coeffs(c3, c2, c1, c0, c, a0, a1, a2, a3)) { bail = true; return; }
   cubic_apply(D, a0, a1, a2, a3, y0);
   cubic_apply(D, a0, a1, a2, a3, y1);

@@ -93,7 +93,7 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 template <typename T, bool STABLE, bool NM, bool EXTRAS, bool FAST = false>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
                                             ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4],
-                                            bool& bail) {
+                                            bool& bail, bool untilted = true) {
   using namespace ho;
   // isotropic crystal (scalar eps(f), mu(f), e.g. SiC): closed-form modes, no quartic
   const bool iso_crystal = (L.kind == HO_ANISO_FILM || L.kind == HO_ANISO_EXIT) && L.eps_scalar && L.mu_scalar;
@@ -119,14 +119,17 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     // crystal film or crystal exit: one instance of the Delta assembly + spectral split
     ZRow<T> z;
     Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
-    if constexpr (FAST) {
-      if (L.kind == HO_ANISO_FILM) {  // un-tilted crystal film: closed form, no spectral split
-        const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-        film_biquadratic<T, NM, STABLE>(D, mk<T>(T(0), -(k0 * d)), y0, y1, w, bail);
-        return;
-      }
+    cx<T> c3, c2, c1, c0;
+    charpoly(D, c3, c2, c1, c0);
+    if (L.kind == HO_ANISO_FILM && (FAST || untilted)) {
+      // un-tilted thin crystal film: pair-symmetric closed form, no spectral split
+      const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
+      bool general = false;
+      film_biquadratic<T, NM, STABLE>(D, c3, c2, c1, c0, mk<T>(T(0), -(k0 * d)), y0, y1, w, general);
+      if (!general) return;
+      if constexpr (FAST) { bail = true; return; }
     }
-    Spectrum<T> s = split_spectrum<T, NM, FAST>(D, bail);
+    Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail);
     if (L.kind == HO_ANISO_EXIT) {
       substrate_plane(D, s, y0, y1);
       if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
@@ -299,7 +302,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
       cx<T> w[4];
-      apply_layer<T, STABLE, NM, POWER, FAST>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail);
+      apply_layer<T, STABLE, NM, POWER, FAST>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path != 0 && mode != MODE_FIXUP);
       if constexpr (FAST) {
         if (bail) break;
       }
@@ -392,7 +395,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
         for (int l = l_hi; l >= l_lo; --l) {
           cx<T> w[4];
           bool bail = false;  // (general build: never set)
-          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail);
+          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path != 0);
           if constexpr (POWER) {
             flux_form(y0, y1, hf[l]);
             wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];

@@ -52,3 +52,48 @@ def test_model_power_bookkeeping(name):
                 err = np.abs(parity.subsample(present(val), fx["strides"]) - fx[key])
                 err = err[mask] if np.ndim(err) else err
                 assert np.nanmax(err) <= tol, f"{name}/{backend}/{key}: {np.nanmax(err):.2e}"
+
+
+def test_pair_symmetric_film_equals_expm():
+    """Closed form for un-tilted crystal films (tools/algo_model.film_pair_symmetric, the model of
+    ho_berreman.cuh pair_symmetric_film_coeffs) vs scipy's expm on random crystals carrying the
+    reference's hidden tilt (1e-8 .. 1e-6), including near-normal incidence where the root pairs
+    almost merge: accepted points agree to 1e-12, and the acceptance test is not vacuous."""
+    import scipy.linalg as sl
+
+    from tools import algo_model as am
+
+    rng = np.random.default_rng(7)
+
+    def dense(D):
+        a, b, c, d, e, f, g, h, j = D
+        return np.array([[a, b, c, d], [0, e, f, -c], [g, h, e, -b], [j, -g, 0, a]], dtype=complex)
+
+    def rot(axis, t):
+        c, s = np.cos(t), np.sin(t)
+        return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]) if axis == "y" else np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+
+    worst, accepted, total = 0.0, 0, 3000
+    Y = [(1 + 0j, 0j, 0.3 + 0.1j, 0.2j), (0j, 1 + 0j, -0.5 + 0j, 0.7 + 0.2j)]
+    with np.errstate(all="ignore"):
+        for _ in range(total):
+            ex, ey, ez = [complex(rng.normal() * 5, abs(rng.normal()) * rng.choice([1e-3, 0.1, 2])) for _ in range(3)]
+            if rng.random() < 0.4:
+                ey = ex
+            R = rot("z", rng.uniform(0, 6.28) * rng.choice([0, 1])) @ rot("y", 1e-8 * rng.choice([1, 1, 10, 100]))
+            eps = R @ np.diag([ex, ey, ez]) @ R.T
+            k = rng.choice([rng.uniform(0, 3.5), rng.uniform(0, 0.3), 0.0, 1e-3])
+            e = np.array([eps[0, 0], eps[0, 1], eps[0, 2], eps[1, 1], eps[1, 2], eps[2, 2]])
+            D = am.berreman9(k, e, np.array([1, 0, 0, 1, 0, 1], dtype=complex))
+            cf = -1j * rng.choice([1e-4, 1e-2, 0.3, 2.0, 10.0]) * rng.uniform(0.5, 1.5)
+            out, ok = am.film_pair_symmetric(tuple(np.asarray(x) for x in D), Y, cf)
+            if not ok:
+                continue
+            accepted += 1
+            E = sl.expm(cf * dense(D))
+            for col in range(2):
+                ref = E @ np.array(Y[col])
+                got = np.array([complex(x) for x in out[col]])
+                worst = max(worst, np.abs(got - ref).max() / np.abs(ref).max())
+    assert accepted > 0.4 * total
+    assert worst <= 1e-12, worst

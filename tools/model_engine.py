@@ -70,10 +70,25 @@ def run(plan, backend="transfer", stats=None, **kw):
                 spec = am.split_spectrum(D, stats=stats, **kw)
                 if stats is not None:
                     stats.setdefault("n_complex", []).append(spec[4])
+                Y_in = Y
                 if stable:
-                    Y, w = am.film_stable(D, Y, spec[:4], cfac, return_w=True)
+                    Y, w = am.film_stable(D, Y_in, spec[:4], cfac, return_w=True)
                 else:
-                    Y, w = am.film_transfer(D, Y, spec[:4], cfac, return_w=True)
+                    Y, w = am.film_transfer(D, Y_in, spec[:4], cfac, return_w=True)
+                if plan.fast_path:
+                    # un-tilted crystals: the kernels take the pair-symmetric closed form where it applies
+                    Yp, ok = am.film_pair_symmetric(D, Y_in, cfac)
+                    one, zero = np.ones_like(Yp[0][0]), np.zeros_like(Yp[0][0])
+                    wp = ((one, zero), (zero, one))
+                    if stable:
+                        n00, n01, n10, n11 = am._inv2(Yp[0][0], Yp[1][0], Yp[0][1], Yp[1][1])
+                        Yp = [tuple(Yp[0][i] * n00 + Yp[1][i] * n10 for i in range(4)),
+                              tuple(Yp[0][i] * n01 + Yp[1][i] * n11 for i in range(4))]
+                        wp = ((n00, n01), (n10, n11))
+                    Y = [tuple(np.where(ok, Yp[k][i], Y[k][i]) for i in range(4)) for k in range(2)]
+                    w = tuple(tuple(np.where(ok, wp[r][c], w[r][c]) for c in range(2)) for r in range(2))
+                    if stats is not None:
+                        stats.setdefault("pair_symmetric", []).append(float(np.mean(ok)))
             forms.append(am.flux_form(Y)); maps.append(w)
         r_pp, r_ps, r_sp, r_ss = am.reflect_from_plane(
             Y, plan.prism_inv_cos[a], plan.prism_inv_ncos[a], plan.prism_inv_n)
