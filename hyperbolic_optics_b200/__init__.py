@@ -8,9 +8,10 @@ hand-written sm_100a CUDA kernels through the C ABI in ``include/ho_b200.h``.
 from .fields import FieldProfile
 from .materials import create_material, list_materials
 from .mueller import Mueller
+from .jones import Jones, compose_jones
 from .scenario import ScenarioSetup
 from .structure import Structure
 from .sweep import ThicknessSweep
 
 __version__ = "0.1.0"
-__all__ = ["Structure", "ScenarioSetup", "Mueller", "FieldProfile", "ThicknessSweep", "create_material", "list_materials", "__version__"]
+__all__ = ["Structure", "ScenarioSetup", "Mueller", "Jones", "compose_jones", "FieldProfile", "ThicknessSweep", "create_material", "list_materials", "__version__"]

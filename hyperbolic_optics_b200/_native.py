@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 5
+HO_ABI_VERSION = 6
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -60,7 +60,21 @@ class OutputsF32(C.Structure):
     ]
 
 
-EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_measure_fp64_peak", "ho_launch_count",
+class Polarimetry(C.Structure):
+    _fields_ = [
+        ("j_pp", C.c_void_p), ("j_ps", C.c_void_p), ("j_sp", C.c_void_p), ("j_ss", C.c_void_p),
+        ("s_pre", C.c_double * 4), ("m_post", C.c_double * 16),
+        ("e_pre", c128 * 2), ("j_post", c128 * 4),
+        ("stokes", C.c_void_p), ("polarisation", C.c_void_p),
+        ("jones_vector", C.c_void_p), ("jones_stokes", C.c_void_p),
+        ("ellipsometry", C.c_void_p),
+        ("eigenvalues", C.c_void_p), ("eigenvectors", C.c_void_p), ("discriminant", C.c_void_p), ("overlap", C.c_void_p),
+        ("decomposition", C.c_void_p), ("decomposition_matrices", C.c_void_p),
+        ("mueller", C.c_void_p),
+    ]
+
+
+EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_measure_fp64_peak", "ho_launch_count",
            "ho_abi_version", "ho_last_error")
 
 
@@ -80,6 +94,8 @@ def load():
     lib.ho_reflect.restype = C.c_int
     lib.ho_reflect_f32.argtypes = [C.POINTER(Problem), C.POINTER(OutputsF32), C.c_int64, C.c_int64, C.c_void_p]
     lib.ho_reflect_f32.restype = C.c_int
+    lib.ho_polarimetry.argtypes = [C.POINTER(Polarimetry), C.c_int64, C.c_void_p]
+    lib.ho_polarimetry.restype = C.c_int
     lib.ho_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
     lib.ho_measure_fp64_peak.restype = C.c_int
     lib.ho_launch_count.argtypes = []

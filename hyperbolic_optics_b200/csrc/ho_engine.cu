@@ -67,6 +67,12 @@ template <typename T> __device__ __forceinline__ ho::Sym6<T> load_sym(const ho_c
   return s;
 }
 
+}  // namespace
+
+#include "ho_polarimetry.cuh"
+
+namespace {
+
 template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer_delta(const ho_layer_t& L, T k, int f, int b, ho::ZRow<T>& z) {
   using namespace ho;
   int bi = L.n_beta > 1 ? b : 0;
@@ -706,6 +712,24 @@ int ho_measure_fp64_peak(int iters, double* flops_per_s, void* cuda_stream) {
   cudaFree(sink);
   if (err != cudaSuccess) return fail(HO_ERR_CUDA, "fp64 peak kernel failed: %s", cudaGetErrorString(err));
   *flops_per_s = 2.0 * 8.0 * (double)iters * threads * (double)blocks / (ms * 1e-3);
+  return HO_OK;
+}
+
+int ho_polarimetry(const ho_polarimetry_t* q, int64_t n, void* cuda_stream) {
+  if (!q || n < 0) return fail(HO_ERR_BAD_ARGUMENT, "ho_polarimetry: null request or negative n%s");
+  if (n == 0) return HO_OK;
+  if (!q->j_pp || !q->j_ps || !q->j_sp || !q->j_ss) return fail(HO_ERR_BAD_ARGUMENT, "ho_polarimetry: the four Jones planes are required%s");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HO_ERR_NO_DEVICE, "ho_polarimetry: no CUDA device%s");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 2;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polarimetry_kernel, kPolarThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int64_t want = (n + kPolarThreads - 1) / kPolarThreads, cap = (int64_t)sms * per_sm * 8;
+  polarimetry_kernel<<<(int)(want < cap ? want : cap), kPolarThreads, 0, (cudaStream_t)cuda_stream>>>(*q, n);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_polarimetry launch: %s", cudaGetErrorString(err));
+  g_launches.fetch_add(1);
   return HO_OK;
 }
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 5
+#define HO_ABI_VERSION 6
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -141,6 +141,38 @@ typedef struct {
 } ho_outputs_f32_t;
 int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out,
                    int64_t n_begin, int64_t n_end, void* cuda_stream);
+
+/* Polarimetry epilogue over Jones planes that are resident in HBM (the r_ij or t_ij planes of
+   ho_outputs_t, or any other [n] complex128 planes): one pass, 64 B read per point, only the
+   requested planes written.  Replaces the per-point NumPy post-processing of the reference's
+   consumer classes; host code folds the ideal components (polarisers, wave plates, rotators:
+   constant matrices) before / after the sample into s_pre, m_post, e_pre, j_post.
+   All pointers are device pointers; NULL output = not wanted. */
+typedef struct {
+  const ho_c128* j_pp; const ho_c128* j_ps; const ho_c128* j_sp; const ho_c128* j_ss; /* [n] each */
+  /* Mueller chain  s_out = m_post * M(J) * s_pre               mueller.py:446-500 */
+  double s_pre[4];
+  double m_post[16];      /* row-major */
+  /* Jones chain    e_out = j_post * J * e_pre                  jones.py:153-192 */
+  ho_c128 e_pre[2];
+  ho_c128 j_post[4];      /* row-major 2x2 */
+  double* stokes;         /* [4][n] S0..S3 of the Mueller chain                      mueller.py:479-500 */
+  double* polarisation;   /* [3][n] DOP, ellipticity, azimuth of that Stokes vector  mueller.py:516-583 */
+  ho_c128* jones_vector;  /* [2][n] E_p, E_s of the Jones chain                      jones.py:182-192 */
+  double* jones_stokes;   /* [6][n] S0..S3, azimuth, ellipticity of that vector      jones.py:199-226 */
+  double* ellipsometry;   /* [6][n] Psi, Delta, Psi_ps, Delta_ps, Psi_sp, Delta_sp (degrees)  jones.py:290-320 */
+  ho_c128* eigenvalues;   /* [2][n] tr/2 +- sqrt(discriminant) (principal root)      jones.py:228-264 */
+  ho_c128* eigenvectors;  /* [4][n] planes (row, col) = (0,0) (0,1) (1,0) (1,1); column k is the unit
+                             eigenvector of eigenvalue k, largest component real positive (LAPACK) */
+  ho_c128* discriminant;  /* [n]    ((J_pp - J_ss)/2)^2 + J_ps J_sp */
+  double* overlap;        /* [n]    |<v0|v1>| */
+  double* decomposition;  /* [5][n] diattenuation, polarizance, retardance (rad), depolarization,
+                             transmittance of the Lu-Chipman decomposition          mueller.py:368-444 */
+  double* decomposition_matrices; /* [3][n][16] diattenuator, retarder, depolarizer (normalised) */
+  double* mueller;        /* [n][16] Mueller matrix of these Jones planes (e.g. the transmission
+                             Mueller matrix, mueller.py:327-356) */
+} ho_polarimetry_t;
+int ho_polarimetry(const ho_polarimetry_t* request, int64_t n, void* cuda_stream);
 
 /* FP64 FMA-chain microbenchmark used as the roofline denominator: runs `iters` dependent
    FMA rounds on every SM and returns achieved FLOP/s (2 flops per FMA) in *flops_per_s. */

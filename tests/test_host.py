@@ -119,8 +119,8 @@ def test_present_squeezes_like_reference():
 def test_library_exports_every_declared_symbol(built_library):
     header = (ROOT / "include" / "ho_b200.h").read_text()
     declared = set(re.findall(r"\b(ho_[a-z0-9_]+)\s*\(", header))
-    assert {"ho_reflect", "ho_reflect_f32", "ho_measure_fp64_peak", "ho_launch_count", "ho_abi_version",
-            "ho_last_error"} <= declared
+    assert {"ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_measure_fp64_peak", "ho_launch_count",
+            "ho_abi_version", "ho_last_error"} <= declared
     for sym in declared:
         assert hasattr(built_library, sym), f"{sym} declared in ho_b200.h but not exported"
     from hyperbolic_optics_b200 import _native
@@ -141,6 +141,10 @@ def test_descriptor_validation_without_gpu(built_library):
     prob.A = prob.B = prob.F = prob.T = 1
     prob.n_layers = 99
     assert built_library.ho_reflect(ctypes.byref(prob), ctypes.byref(out), 0, 0, None) == -1
+    req = nat.Polarimetry()
+    assert built_library.ho_polarimetry(ctypes.byref(req), 16, None) == -1
+    assert b"Jones planes" in built_library.ho_last_error()
+    assert built_library.ho_polarimetry(ctypes.byref(req), 0, None) == 0  # empty range: nothing to do
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -152,15 +156,17 @@ def test_struct_layout_matches_header(tmp_path):
     probe = tmp_path / "probe.c"
     probe.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "ho_b200.h"\n'
-        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ho_layer_t), sizeof(ho_problem_t), '
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ho_layer_t), sizeof(ho_problem_t), '
         'offsetof(ho_problem_t, layers), offsetof(ho_layer_t, eps), offsetof(ho_layer_t, exit_n), '
-        'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_pp)); return 0; }\n')
+        'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_pp), sizeof(ho_polarimetry_t), '
+        'offsetof(ho_polarimetry_t, j_post), offsetof(ho_polarimetry_t, mueller)); return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [ctypes.sizeof(nat.LayerDesc), ctypes.sizeof(nat.Problem), nat.Problem.layers.offset,
                    nat.LayerDesc.eps.offset, nat.LayerDesc.exit_n.offset, ctypes.sizeof(nat.Outputs),
-                   nat.Outputs.t_pp.offset]
+                   nat.Outputs.t_pp.offset, ctypes.sizeof(nat.Polarimetry), nat.Polarimetry.j_post.offset,
+                   nat.Polarimetry.mueller.offset]
 
 
 def test_product_never_imports_oracle():
