@@ -722,11 +722,13 @@ int ho_polarimetry(const ho_polarimetry_t* q, int64_t n, void* cuda_stream) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(HO_ERR_NO_DEVICE, "ho_polarimetry: no CUDA device%s");
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool decomp = q->decomposition || q->decomposition_matrices;
+  auto kern = decomp ? polarimetry_kernel<true> : polarimetry_kernel<false>;
   int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polarimetry_kernel, kPolarThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPolarThreads, 0);
   if (per_sm < 1) per_sm = 1;
   int64_t want = (n + kPolarThreads - 1) / kPolarThreads, cap = (int64_t)sms * per_sm * 8;
-  polarimetry_kernel<<<(int)(want < cap ? want : cap), kPolarThreads, 0, (cudaStream_t)cuda_stream>>>(*q, n);
+  kern<<<(int)(want < cap ? want : cap), kPolarThreads, 0, (cudaStream_t)cuda_stream>>>(*q, n);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_polarimetry launch: %s", cudaGetErrorString(err));
   g_launches.fetch_add(1);

@@ -162,7 +162,10 @@ constexpr int kPolarThreads = 256;
 
 __device__ __forceinline__ void st_plain(ho_c128* p, ho::cx<double> v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
 
-__global__ void __launch_bounds__(kPolarThreads, 2)
+// DECOMP: the Lu-Chipman branch is compiled in (128 registers, 2 CTAs/SM); the light build
+// without it fits 3 CTAs/SM, which the streaming requests need to cover the HBM latency.
+template <bool DECOMP>
+__global__ void __launch_bounds__(kPolarThreads, DECOMP ? 2 : 3)
 polarimetry_kernel(const __grid_constant__ ho_polarimetry_t q, int64_t n) {
   using namespace ho;
   typedef cx<double> C;
@@ -170,7 +173,7 @@ polarimetry_kernel(const __grid_constant__ ho_polarimetry_t q, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const C pp = ldc<double>(q.j_pp + i), ps = ldc<double>(q.j_ps + i);
     const C sp = ldc<double>(q.j_sp + i), ss = ldc<double>(q.j_ss + i);
-    const bool want_m = q.stokes || q.polarisation || q.decomposition || q.decomposition_matrices || q.mueller;
+    const bool want_m = q.stokes || q.polarisation || q.mueller || (DECOMP && (q.decomposition || q.decomposition_matrices));
     if (want_m) {
       double M[16];
       mueller_from_jones(pp, ps, sp, ss, M);
@@ -197,7 +200,7 @@ polarimetry_kernel(const __grid_constant__ ho_polarimetry_t q, int64_t n) {
           q.polarisation[2 * n + i] = 0.5 * atan2(s[2], s[1]);
         }
       }
-      if (q.decomposition || q.decomposition_matrices) {
+      if (DECOMP && (q.decomposition || q.decomposition_matrices)) {
         double sc[5];
         lu_chipman(M, sc, q.decomposition_matrices, n, i);
         if (q.decomposition) {
