@@ -652,7 +652,7 @@ template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ voi
 }
 
 // Fast-path film: the pair-symmetric form above, then (stable recursion) the same re-basing as film_stable
-template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_biquadratic(const Delta<T, NM>& D, cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_pair_symmetric(const Delta<T, NM>& D, cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> a0, a1, a2, a3;
   if (!pair_symmetric_film_coeffs(c3, c2, c1, c0, c, a0, a1, a2, a3)) { bail = true; return; }
   cubic_apply(D, a0, a1, a2, a3, y0);

@@ -90,6 +90,9 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 #ifndef HO_MIN_BLOCKS
 #define HO_MIN_BLOCKS 3
 #endif
+#ifndef HO_FAST_BLOCKS
+#define HO_FAST_BLOCKS 3
+#endif
 
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
 // the stable recursion (power bookkeeping only; dead code otherwise).
@@ -131,7 +134,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
       // un-tilted thin crystal film: pair-symmetric closed form, no spectral split
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       bool general = false;
-      film_biquadratic<T, NM, STABLE>(D, c3, c2, c1, c0, mk<T>(T(0), -(k0 * d)), y0, y1, w, general);
+      film_pair_symmetric<T, NM, STABLE>(D, c3, c2, c1, c0, mk<T>(T(0), -(k0 * d)), y0, y1, w, general);
       if (!general) return;
       if constexpr (FAST) { bail = true; return; }
     }
@@ -261,7 +264,7 @@ enum { MODE_ALL = 0, MODE_FIXUP = 1 };
 // FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only the deferred points.
 // work[0] = number of deferred points, work[1 .. cap] = their indices relative to n_begin.
 template <typename T, bool STABLE, bool NM, bool POWER, bool FAST>
-__global__ void __launch_bounds__(kThreads, HO_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, FAST ? HO_FAST_BLOCKS : HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
                unsigned* work, unsigned cap) {
   using namespace ho;
