@@ -93,6 +93,9 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 #ifndef HO_FAST_BLOCKS
 #define HO_FAST_BLOCKS 3
 #endif
+#ifndef HO_SWEEP_BLOCKS
+#define HO_SWEEP_BLOCKS 2
+#endif
 
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
 // the stable recursion (power bookkeeping only; dead code otherwise).
@@ -346,10 +349,13 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
 //   pass 1..  : lane <-> point (32 consecutive points per pass: coalesced stores).  Fetch the
 //               group's plane from shared memory, apply the swept layer and the layers above it.
 // Both kinds of pass run through the same instance of the layer code (one loop body).
+// Launch shape 128 x 2 CTAs/SM (254 registers, no spills): measured on C5 against 128 x 4 (128
+// registers, 1.3-1.8 KB of spills per thread) and 128 x 3 (168 registers, 150-800 B): 2.52 / 2.94 /
+// 3.13 ms for the scaled sweep without power planes, 5.77 / 6.19 / 6.84 ms with them.
 constexpr int kSweepThreads = 128;
 
 template <bool STABLE, bool NM, bool POWER>
-__global__ void __launch_bounds__(kSweepThreads, 4)
+__global__ void __launch_bounds__(kSweepThreads, HO_SWEEP_BLOCKS)
 tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64_t n_begin, int64_t n_end,
               int swept, int gpw, int row) {
   using namespace ho;
