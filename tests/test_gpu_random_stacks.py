@@ -224,3 +224,79 @@ def test_complex64_option_on_random_stacks(built_library):
     assert total > 15000 and ok / total >= 0.999, f"{ok}/{total} within 1e-4"
     with pytest.raises(ValueError):
         Structure(device="cuda:0").execute(payload, precision="complex64", power=True)
+
+
+def untilted_case(seed):
+    """Random stacks whose crystals all keep z as a principal axis (rotationX = 0, rotationY in
+    {0, 90, 180}, any rotationZ): the plans that carry ``fast_path`` and therefore take the
+    pair-symmetric closed-form film and -- when forced -- the fast-path / fix-up protocol.
+    Includes normal incidence columns (the +-mu pairs merge: the point must fall back), thick films
+    (must fall back) and thickness sweeps."""
+    rng = np.random.default_rng(seed)
+    names = ["Quartz", "Calcite", "hBN", "SiC", "MoO3", "AlN", "GaN", "Sapphire"]
+    n_films = int(rng.integers(1, 4))
+    mats = [names[int(rng.integers(len(names)))] for _ in range(n_films + 1)]
+    lo = max(MATERIALS[m][0] for m in mats)
+    hi = min(MATERIALS[m][1] for m in mats)
+    if not lo < hi:
+        lo, hi = MATERIALS[mats[0]]
+    layers = [P.prism(float(rng.uniform(2.0, 50.0)))]
+    if rng.random() < 0.5:
+        layers.append(P.gap(float(10 ** rng.uniform(-2, 0.3)), float(rng.uniform(1.0, 3.0))))
+    for m in mats[:-1]:
+        layers.append(P.film(m, float(10 ** rng.uniform(-2.5, 1.0)), rx=0.0, ry=float(rng.choice([0.0, 90.0, 180.0])),
+                             rz=float(rng.uniform(0.0, 180.0)), ztype="static" if rng.random() < 0.25 else None))
+    if rng.random() < 0.7:
+        layers.append(P.substrate(mats[-1], rx=0.0, ry=float(rng.choice([0.0, 90.0])), rz=float(rng.uniform(0.0, 180.0))))
+    else:
+        layers.append(P.iso_exit(float(rng.uniform(1.0, 12.0))))
+    if rng.random() < 0.25:
+        i = [k for k, layer in enumerate(layers) if layer["type"] == "Crystal Layer"][0]
+        layers[i]["thickness"] = [float(x) for x in 10 ** np.sort(rng.uniform(-2, 0.6, 4))]
+    kind = ["Incident", "Azimuthal", "Dispersion", "FullSweep"][int(rng.integers(4))]
+    freqs = list(np.sort(rng.uniform(lo, hi, int(rng.integers(2, 6)))))
+    if kind == "Incident":
+        sd, grid = {"type": kind, "frequency": freqs}, dict(A=25)   # odd: theta = 0 is on the grid
+    elif kind == "Azimuthal":
+        sd, grid = {"type": kind, "incidentAngle": float(rng.choice([1e-4, 0.5, 30.0, 70.0])), "frequency": freqs}, dict(B=24)
+    elif kind == "Dispersion":
+        sd, grid = {"type": kind, "frequency": float(freqs[0])}, dict(A=12, B=12)
+    else:
+        sd, grid = {"type": kind, "frequency": freqs}, dict(A=8, B=8)
+    return {"payload": {"ScenarioData": sd, "Layers": layers}, "grid": grid}
+
+
+@pytest.mark.parametrize("forced", ["default", "fast-path protocol"])
+@pytest.mark.parametrize("block", range(3))
+def test_untilted_random_stacks_match_oracle(block, forced, built_library, monkeypatch):
+    from hyperbolic_optics_b200 import engine
+    from oracle import reference_port as oracle
+
+    if forced != "default":
+        monkeypatch.setenv("HO_B200_FAST_PATH", "1")
+    worst, hinted, two_launch = 0.0, 0, 0
+    for seed in range(3000 + 25 * block, 3000 + 25 * (block + 1)):
+        entry = untilted_case(seed)
+        inc, az = P.angle_overrides(entry)
+        try:
+            ref = oracle.run(entry["payload"], backend="scattering", incident_angle=inc, azimuthal_angle=az)
+        except np.linalg.LinAlgError:
+            continue
+        for backend in ("scattering", "transfer"):
+            before = engine.launch_count()
+            s = _gpu(entry, backend)
+            launches = engine.launch_count() - before
+            hinted += bool(s.plan.fast_path)
+            two_launch += launches >= 3          # fast + fix-up (+ the power launch of _gpu)
+            got = {k: getattr(s, k) for k in parity.R_KEYS}
+            assert np.shape(got["r_pp"]) == np.shape(ref["r_pp"]), f"seed {seed}"
+            err = parity.jones_error(got, ref)
+            ok = np.isfinite(err)
+            if backend == "scattering":
+                assert np.isfinite(np.stack([got[k] for k in parity.R_KEYS])).all(), f"seed {seed}: non-finite stable result"
+                assert ok.mean() > 0.9, f"seed {seed}"
+            if ok.any():
+                assert err[ok].max() <= 1e-9, f"seed {seed} {backend}: {err[ok].max():.3e}\n{entry['payload']}"
+                worst = max(worst, float(err[ok].max()))
+    assert hinted >= 40   # every stack of this generator is un-tilted
+    print(f"block {block} ({forced}): worst Jones rel err {worst:.2e}, {hinted} hinted runs, {two_launch} two-launch runs")
