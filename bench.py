@@ -384,7 +384,9 @@ def run_b200_arm(args, rank, local_rank, world):
             "frac": achieved_tf / (fp64_peak / 1e12),
             "traffic": traffic * n_local if traffic else None,
             "traffic_source": ncu.get("source"),
-            "kernel": "reflect_kernel<double, transfer, non-magnetic>", "kernel_ms": kernel_ms,
+            "kernel": "reflect_kernel<double, transfer, non-magnetic, FAST> + its fix-up pass "
+                      "(reflect_kernel<..., general> over the work list of deferred points, ~5 % of the step)",
+            "kernel_ms": kernel_ms,
             "flops_per_point": FLOPS_PER_POINT,
             "flops_note": "achieved = SURVEY 8d algorithmic work W (7.7 kflop/point for film + substrate) x points / "
                           "kernel time; the kernel reaches it with fewer executed instructions (structure-aware "
