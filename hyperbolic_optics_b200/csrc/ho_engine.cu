@@ -100,7 +100,8 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
 // the stable recursion (power bookkeeping only; dead code otherwise).
 // binv (EXTRAS): kernel exit basis -> the reference's exit-mode amplitudes (transmission coefficients).
-// FAST: fast-path build of the layer code (biquadratic start, thin-film cubic only); sets `bail`
+// FAST: fast-path build of the layer code (biquadratic start for exits, pair-symmetric closed form
+// for films, closed-form isotropic layers; no Ferrari, no block film); sets `bail`
 // when the point needs the general paths.
 template <typename T, bool STABLE, bool NM, bool EXTRAS, bool FAST = false>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
@@ -241,8 +242,9 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
 }
 
 // Fast-path / fix-up protocol (two launches on the same stream, no host round trip):
-//   1. the FAST build of the kernel -- only the biquadratic start and the thin-film cubic are
-//      compiled in: 160 registers without spills and 40 % less code than the general build --
+//   1. the FAST build of the kernel -- only the biquadratic start (exits) and the pair-symmetric
+//      closed form (films) are compiled in: 166-168 registers without spills and 30 % less code
+//      than the general build --
 //      evaluates every point it can; where it cannot it stores a sentinel NaN in r_pp and appends
 //      the point to a work list (warp-aggregated atomic on a counter in stream-ordered scratch);
 //   2. the general build runs in fix-up mode over the compacted list: full warps of deferred
