@@ -42,6 +42,7 @@ template <typename T> struct OutPtrs {
   T s_in[4];
   T* power; int64_t power_stride;
   ho::cx<T>* t_pp; ho::cx<T>* t_ps; ho::cx<T>* t_sp; ho::cx<T>* t_ss;
+  T* t_mode; int64_t t_mode_stride;
 };
 
 template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p) {
@@ -199,6 +200,15 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
       const bool smat = STABLE && crystal_exit;
       if (pol == 0) { st_stream((smat ? out.t_pp : out.t_ps) + o, e0); st_stream((smat ? out.t_ps : out.t_pp) + o, e1); }
       else          { st_stream((smat ? out.t_sp : out.t_ss) + o, e0); st_stream((smat ? out.t_ss : out.t_sp) + o, e1); }
+      if (out.t_mode) {
+        // flux carried by each exit mode alone: its amplitude mapped back to the exit coordinates
+        cx<T> i00, i01, i10, i11;
+        inv2(binv[0], binv[1], binv[2], binv[3], i00, i01, i10, i11);
+        const T* hx = (P.n_layers - 1 < n_upper) ? hf[P.n_layers - 1] : lower + 4 * (P.n_layers - 1 - n_upper);
+        T* tm = out.t_mode + (int64_t)(2 * pol) * out.t_mode_stride + o;
+        st_stream(tm, flux_eval(hx, i00 * e0, i10 * e0) * inv_sinc);
+        st_stream(tm + out.t_mode_stride, flux_eval(hx, i01 * e1, i11 * e1) * inv_sinc);
+      }
     }
   }
 }
@@ -674,6 +684,10 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
   o.t_ss = reinterpret_cast<ho::cx<double>*>(out->t_ss);
   if ((o.t_pp || o.t_ps || o.t_sp || o.t_ss) && !(o.t_pp && o.t_ps && o.t_sp && o.t_ss))
     return fail(HO_ERR_BAD_ARGUMENT, "t_pp, t_ps, t_sp, t_ss must be given together");
+  o.t_mode = out->t_mode;
+  o.t_mode_stride = out->t_mode_stride;
+  if (o.t_mode && !o.t_pp) return fail(HO_ERR_BAD_ARGUMENT, "t_mode needs the t_pp .. t_ss outputs");
+  if (o.t_mode && o.t_mode_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "t_mode_stride is smaller than the point range");
   if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<double, true>(problem, o, n_begin, n_end, s)
@@ -695,6 +709,8 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.power = nullptr;
   o.power_stride = 0;
   o.t_pp = o.t_ps = o.t_sp = o.t_ss = nullptr;
+  o.t_mode = nullptr;
+  o.t_mode_stride = 0;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, n_begin, n_end, s)
                                                    : launch<float, false>(problem, o, n_begin, n_end, s);

@@ -123,11 +123,13 @@ class DeviceOutputs:
         # power bookkeeping planes [2 * (n_layers + 1)][n]: per polarisation R, T, A_0 .. A_{L-2}
         self.power = torch.empty((power_planes, n), dtype=real, device=device) if power_planes else None
         self.t = torch.empty((4, n), dtype=dtype, device=device) if transmission else None  # rows: pp, ps, sp, ss
+        # mode-resolved transmittance planes: (p inc, s-like mode), (p, p-like), (s, s-like), (s, p-like)
+        self.t_mode = torch.empty((4, n), dtype=real, device=device) if transmission else None
 
     @property
     def nbytes(self):
         total = self.r.numel() * self.r.element_size()
-        for t in (self.mueller, self.stokes, self.power, self.t):
+        for t in (self.mueller, self.stokes, self.power, self.t, self.t_mode):
             if t is not None:
                 total += t.numel() * t.element_size()
         return total
@@ -158,6 +160,7 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
             o.power, o.power_stride = out.power.data_ptr(), out.power.shape[1]
         if out.t is not None and select != "power":
             o.t_pp, o.t_ps, o.t_sp, o.t_ss = (out.t[i].data_ptr() for i in range(4))
+            o.t_mode, o.t_mode_stride = out.t_mode.data_ptr(), out.t_mode.shape[1]
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:
         o = nat.OutputsF32()

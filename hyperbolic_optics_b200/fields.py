@@ -8,13 +8,30 @@ registers/local memory and evaluated for unit p and s incidence, so -- unlike th
 whose ``FieldProfile`` needs the transfer matrix (``fields.py:87-88``) -- this works for the
 stable (scattering) backend too.
 
-Not mirrored: depth-resolved ``field_profile`` / ``polarization_resolved`` (single-point tools
-that need LAPACK-convention eigenvectors; DESIGN.md "next").
+``polarization_resolved`` (``fields.py:286-356``): the co- / cross-polarised split of R (from
+``r_ij``) and of T (mode-resolved transmittance planes the kernel writes next to ``t_ij``).
+
+Not mirrored: depth-resolved ``field_profile`` / ``stokes_from_field_profile`` (single-point
+tools; DESIGN.md "next").
 """
 
 from __future__ import annotations
 
 import numpy as np
+import torch
+
+
+def _abs2(x):
+    return x.abs() ** 2 if isinstance(x, torch.Tensor) else np.abs(x) ** 2
+
+
+def _fraction(cross, co):
+    """cross / (co + cross), 0 where there is no light at all (``fields.py:343-345``)."""
+    total = co + cross
+    if isinstance(total, torch.Tensor):
+        return torch.where(total.abs() > 1e-30, cross / total, torch.zeros_like(total))
+    with np.errstate(all="ignore"):
+        return np.where(np.abs(total) > 1e-30, cross / total, 0.0)
 
 
 class FieldProfile:
@@ -41,6 +58,29 @@ class FieldProfile:
         ``Structure.calculate_transmissivity``)."""
         self.structure.calculate_transmissivity()
         return {k: getattr(self.structure, k) for k in ("t_ss", "t_ps", "t_sp", "t_pp")}
+
+    def polarization_resolved(self, polarization="p"):
+        """Experimental in the reference too (``fields.py:286-356``): R and T split into the
+        co-polarised channel (same polarisation as the incident light) and the cross-polarised one
+        (the power analogue of ``r_ps`` / ``t_ps``).  Reflection: ``|r_co|^2``, ``|r_cross|^2``.
+        Transmission: the flux each of the two forward exit modes (index 0 s-like, 1 p-like) carries
+        alone -- exact for an isotropic exit, an eigenmode-resolved approximation for a crystal
+        exit (non-orthogonal modes: ``T_co + T_cross`` need not equal ``T``), as in the reference."""
+        key = polarization.lower() if isinstance(polarization, str) else None
+        if key not in ("p", "s"):
+            raise ValueError("polarization_resolved requires pure 'p' or 's' incidence.")
+        s = self.structure
+        if getattr(s, "mode_transmittance", None) is None:
+            s.t_pp = None  # force the re-launch that also fills the mode-resolved planes
+            s.calculate_transmissivity()
+        modes = s.mode_transmittance[key]
+        if key == "p":
+            r_co, r_cross, t_co, t_cross = _abs2(s.r_pp), _abs2(s.r_ps), modes["p"], modes["s"]
+        else:
+            r_co, r_cross, t_co, t_cross = _abs2(s.r_ss), _abs2(s.r_sp), modes["s"], modes["p"]
+        return {"R_co": r_co, "R_cross": r_cross, "T_co": t_co, "T_cross": t_cross,
+                "conversion_reflection": _fraction(r_cross, r_co),
+                "conversion_transmission": _fraction(t_cross, t_co)}
 
     def layer_absorption(self, polarization="p"):
         blk = self._block(polarization)

@@ -62,6 +62,7 @@ class Structure:
         self.k_0 = None
         self.r_pp = self.r_ss = self.r_ps = self.r_sp = None
         self.t_pp = self.t_ss = self.t_ps = self.t_sp = None
+        self.mode_transmittance = None
         self.transfer_matrix = None
         self.mueller = None
         self.stokes = None
@@ -196,7 +197,7 @@ class Structure:
                                        transmission=self.with_transmission, dtype=cdtype)
             launch(out, base, base + n)
             r = out.r.reshape((4,) + shape)
-            self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False)
+            self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False, tmode=out.t_mode)
             self.d2h_bytes = 0
             return
         # host results: kernel -> device chunk (double buffered) -> pinned host, D2H on a copy stream
@@ -206,6 +207,7 @@ class Structure:
         host_s = _pinned("s", (n, 4), torch.float64) if want_stokes else None
         host_p = _pinned("p", (planes, n), torch.float64) if planes else None
         host_t = _pinned("t", (4, n), torch.complex128) if self.with_transmission else None
+        host_tm = _pinned("tm", (4, n), torch.float64) if self.with_transmission else None
         bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
                                      transmission=self.with_transmission, dtype=cdtype)
                 for _ in range(2 if n > chunk else 1)]
@@ -234,16 +236,17 @@ class Structure:
                 if host_t is not None:
                     for i in range(4):
                         host_t[i, start:stop].copy_(buf.t[i, :m], non_blocking=True)
+                        host_tm[i, start:stop].copy_(buf.t_mode[i, :m], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             done[ci % len(bufs)] = ev
         copy.synchronize()
         scale = 2 if self.precision == "complex128" else 1
         self.d2h_bytes = n * ((32 + (64 if host_m is not None else 0)) * scale
-                              + (32 if host_s is not None else 0) + 8 * planes + (64 if host_t is not None else 0))
-        self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, host_t, shape, to_numpy=True)
+                              + (32 if host_s is not None else 0) + 8 * planes + (96 if host_t is not None else 0))
+        self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, host_t, shape, to_numpy=True, tmode=host_tm)
 
-    def _assign(self, r, mueller, stokes, power, trans, shape, to_numpy):
+    def _assign(self, r, mueller, stokes, power, trans, shape, to_numpy, tmode=None):
         if to_numpy:
             conv = (lambda t: np.array(t.numpy())) if self.own_results else (lambda t: t.numpy())
         else:
@@ -257,6 +260,11 @@ class Structure:
             self.t_pp, self.t_ps, self.t_sp, self.t_ss = (pres(conv(t4[i])) for i in range(4))
         else:
             self.t_pp = self.t_ps = self.t_sp = self.t_ss = None
+        # per incidence ("p", "s"): transmittance carried by the s-like and the p-like exit mode
+        self.mode_transmittance = None
+        if tmode is not None:
+            tm = [pres(conv(tmode[i].reshape(shape))) for i in range(4)]
+            self.mode_transmittance = {"p": {"s": tm[0], "p": tm[1]}, "s": {"s": tm[2], "p": tm[3]}}
         self.power = None
         if power is not None:
             # planes per polarisation: R, T, A_0 .. A_{L-2}  (include/ho_b200.h, ho_outputs_t.power)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 6
+#define HO_ABI_VERSION 7
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -124,6 +124,12 @@ typedef struct {
   ho_c128* t_ps;
   ho_c128* t_sp;
   ho_c128* t_ss;
+  /* Mode-resolved transmittance (needs the t_* outputs): 4 planes of t_mode_stride doubles, plane
+     2*pol + k with pol 0 = p, 1 = s incidence and k = 0: the s-like, k = 1: the p-like forward exit
+     mode; value = S_z(amplitude_k * mode_k) / S_inc.  Replaces the per-mode flux of
+     FieldProfile.polarization_resolved (fields.py:286-356; its T_co / T_cross).  NULL to skip. */
+  double* t_mode;
+  int64_t t_mode_stride; /* >= n_end - n_begin */
 } ho_outputs_t;
 
 /* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /

@@ -572,7 +572,13 @@ def power_summary(layers, gamma, polarization="p"):
     r = 1.0 - _sz(fields[1]) / s_inc
     t = _sz(fields[-1]) / s_inc
     absorbed = [(_sz(fields[i]) - _sz(fields[i + 1])) / s_inc for i in range(1, n - 1)]
-    return {"R": r, "T": t, "A": absorbed}
+    # polarization_resolved (fields.py:286-356): reflected amplitudes = backward slots of
+    # Gamma c_exit; transmitted flux of each forward exit mode alone (slot 0 s-like, slot 2 p-like)
+    c_inc = np.squeeze(gamma @ c_exit[..., None], -1)
+    exit_m = layers[n - 1].matrix
+    t_mode = [_sz(exit_m[..., :, k] * c_exit[..., k, None]) / s_inc for k in (0, 2)]
+    refl = {"s": np.abs(c_inc[..., 1]) ** 2, "p": np.abs(c_inc[..., 3]) ** 2}
+    return {"R": r, "T": t, "A": absorbed, "T_mode": {"s": t_mode[0], "p": t_mode[1]}, "R_mode": refl}
 
 
 def run(payload, backend="transfer", incident_angle=None, azimuthal_angle=None,
@@ -598,6 +604,9 @@ def run(payload, backend="transfer", incident_angle=None, azimuthal_angle=None,
                 ps = power_summary(st["layers"], gamma, pol)
                 out[f"R_{pol}"], out[f"T_{pol}"] = present(ps["R"]), present(ps["T"])
                 out[f"A_{pol}"] = [present(a) for a in ps["A"]]
+                other = "s" if pol == "p" else "p"
+                out[f"pr_{pol}"] = {"R_co": present(ps["R_mode"][pol]), "R_cross": present(ps["R_mode"][other]),
+                                    "T_co": present(ps["T_mode"][pol]), "T_cross": present(ps["T_mode"][other])}
     out["stack"] = st
     out["transfer_matrix"] = gamma
     return out

@@ -11,7 +11,8 @@ backend, ``make_fixtures.run_reference``) and its ``Mueller`` / ``Jones`` classe
 * two Mueller component chains (incident state, ideal components before / after the sample),
 * the transmission Mueller matrix, the Lu-Chipman decomposition of the reflection matrix,
 * one Jones component chain (vector, intensity, Stokes, ellipse),
-* eigenpolarisations, ellipsometric angles, the exceptional-point scan.
+* eigenpolarisations, ellipsometric angles, the exceptional-point scan,
+* ``FieldProfile.polarization_resolved`` for p and s incidence (reference ``fields.py:286-356``).
 
 A strided sample of the inputs (``r_*``, ``t_*``) and of every output goes to
 ``tests/golden/polarimetry_<name>.npz`` (all of these are per-point functions of the Jones
@@ -31,6 +32,7 @@ sys.path.insert(0, str(HERE.parent.parent))
 sys.path.insert(0, "/root/reference")
 sys.dont_write_bytecode = True
 
+from hyperbolic_optics.fields import FieldProfile  # noqa: E402  (reference)
 from hyperbolic_optics.jones import Jones  # noqa: E402  (reference)
 from hyperbolic_optics.mueller import Mueller  # noqa: E402  (reference)
 
@@ -84,6 +86,11 @@ def build(name):
         out["eig_t_overlap"] = sample(eig_t["eigenvector_overlap"], strides)
         for key, val in Jones(st).ellipsometric_parameters().items():
             out[f"ell_{key}"] = sample(val, strides)
+        fp = FieldProfile(st)
+        for pol in "ps":
+            for key, val in fp.polarization_resolved(pol).items():
+                out[f"pr_{pol}_{key}"] = sample(val, strides)
+            out[f"pr_{pol}_T"] = sample(fp.transmittance(pol), strides)
         ep = Jones(st).find_exceptional_points(0.9)
         out["ep_near"] = sample(ep["near_ep"], strides)
         out["ep_index"] = np.array(ep["ep_index"], dtype=np.int64)

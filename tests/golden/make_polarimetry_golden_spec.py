@@ -1,7 +1,8 @@
 """Which payloads and which component chains the polarimetry fixtures cover (shared by the
 generator, which needs the reference, and the tests, which must not)."""
 
-NAMES = ["simple_calcite", "incident_calcite", "azimuthal_calcite", "fullsweep_quartz", "c2_dispersion_moo3"]
+NAMES = ["simple_calcite", "incident_calcite", "azimuthal_calcite", "fullsweep_quartz", "c2_dispersion_moo3",
+         "dispersion_iso_exit", "multilayer_incident"]
 
 # (incident state, components in beam order); "sample" marks the structure
 MUELLER_CHAINS = {

@@ -405,3 +405,42 @@ def test_mueller_behaviour(built_library):
     assert np.abs(refl - np.abs(si.r_sp) ** 2).max() <= 1e-12
     dec = Mueller(si).decompose()
     assert dec["retardance"].shape == (410, 360) and dec["retarder"].shape == (410, 360, 4, 4)
+
+
+@pytest.mark.parametrize("backend", ["transfer", "scattering"])
+@pytest.mark.parametrize("name", ["simple_calcite", "incident_calcite", "azimuthal_calcite", "fullsweep_quartz",
+                                  "c2_dispersion_moo3", "dispersion_iso_exit", "multilayer_incident"])
+def test_polarization_resolved(name, backend, built_library):
+    """FieldProfile.polarization_resolved (mode-resolved transmittance planes of the kernel, both
+    recursions) vs the reference's (transfer-only) values; plus its own invariants."""
+    from hyperbolic_optics_b200 import FieldProfile
+
+    fx = load(name)
+    s = _run_gpu(name, backend, with_power=True, with_transmission=True)
+    fp = FieldProfile(s)
+    with pytest.raises(ValueError):
+        fp.polarization_resolved((1.0, 1.0))
+    strides = fx["strides"]
+    # the reference's transfer walk is only sound where its own r and its power walk agree
+    for pol in "ps":
+        res = fp.polarization_resolved(pol)
+        assert set(res) == {"R_co", "R_cross", "T_co", "T_cross", "conversion_reflection", "conversion_transmission"}
+        ref_ok = np.isfinite(fx[f"pr_{pol}_T_co"]) & np.isfinite(fx[f"pr_{pol}_R_co"])
+        co = "r_pp" if pol == "p" else "r_ss"
+        ref_ok &= np.abs(fx[f"pr_{pol}_R_co"] - np.abs(fx[co]) ** 2) <= 1e-9   # reference self-consistency
+        assert ref_ok.mean() > 0.7
+        for key in ("R_co", "R_cross", "T_co", "T_cross"):
+            err = np.abs(_sampled(res[key], strides) - fx[f"pr_{pol}_{key}"])[ref_ok]
+            # the per-mode split of T rests on the individual exit eigenvectors, conditioned by the
+            # gap of the two forward eigenvalues like t_ij (1e-7 there, test_transmission_coefficients)
+            tol = 1e-8 if key.startswith("R") else 1e-6
+            assert err.max() <= tol, f"{name}/{backend}/{pol}/{key}: {err.max():.2e}"
+            assert np.median(err) <= 1e-12
+        # co + cross reflectance is the flux reflectance
+        assert np.abs(_sampled(res["R_co"] + res["R_cross"], strides) - _sampled(fp.reflectance(pol), strides))[ref_ok].max() <= 1e-8
+        frac = _sampled(res["conversion_reflection"], strides)
+        assert ((frac >= 0) & (frac <= 1 + 1e-12))[np.isfinite(frac)].all()
+    if name in ("dispersion_iso_exit",):  # isotropic exit: the two modes are orthogonal, the split is exact
+        for pol in "ps":
+            res = fp.polarization_resolved(pol)
+            assert np.abs(np.asarray(res["T_co"]) + np.asarray(res["T_cross"]) - np.asarray(fp.transmittance(pol))).max() <= 1e-10

@@ -158,14 +158,14 @@ def test_struct_layout_matches_header(tmp_path):
         '#include <stdio.h>\n#include <stddef.h>\n#include "ho_b200.h"\n'
         'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ho_layer_t), sizeof(ho_problem_t), '
         'offsetof(ho_problem_t, layers), offsetof(ho_layer_t, eps), offsetof(ho_layer_t, exit_n), '
-        'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_pp), sizeof(ho_polarimetry_t), '
+        'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_mode), sizeof(ho_polarimetry_t), '
         'offsetof(ho_polarimetry_t, j_post), offsetof(ho_polarimetry_t, mueller)); return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [ctypes.sizeof(nat.LayerDesc), ctypes.sizeof(nat.Problem), nat.Problem.layers.offset,
                    nat.LayerDesc.eps.offset, nat.LayerDesc.exit_n.offset, ctypes.sizeof(nat.Outputs),
-                   nat.Outputs.t_pp.offset, ctypes.sizeof(nat.Polarimetry), nat.Polarimetry.j_post.offset,
+                   nat.Outputs.t_mode.offset, ctypes.sizeof(nat.Polarimetry), nat.Polarimetry.j_post.offset,
                    nat.Polarimetry.mueller.offset]
 
 

@@ -72,3 +72,24 @@ def test_error_contract():
         pp.incident_stokes("radial")
     with pytest.raises(ValueError):
         pp.incident_jones("radial")
+
+
+@pytest.mark.parametrize("name", ["simple_calcite", "incident_calcite", "dispersion_iso_exit", "c2_dispersion_moo3"])
+def test_polarization_resolved_port(name):
+    """oracle/reference_port.power_summary's co / cross split (R from the backward slots of
+    Gamma c_exit, T from the flux of each forward exit mode alone) vs the reference's
+    FieldProfile.polarization_resolved (fields.py:286-356)."""
+    from oracle import reference_port as oracle
+    from tests.golden.payloads import ALL, angle_overrides
+    from tests.parity import subsample
+
+    fx = load(name)
+    entry = ALL[name]
+    inc, az = angle_overrides(entry)
+    out = oracle.run(entry["payload"], incident_angle=inc, azimuthal_angle=az, with_power=True)
+    for pol in "ps":
+        for key in ("R_co", "R_cross", "T_co", "T_cross"):
+            got = subsample(np.asarray(out[f"pr_{pol}"][key]), fx["strides"])
+            ref = fx[f"pr_{pol}_{key}"]
+            fin = np.isfinite(ref)
+            assert np.abs(got - ref)[fin].max() <= 1e-12, f"{pol}/{key}"
