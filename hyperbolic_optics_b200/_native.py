@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 7
+HO_ABI_VERSION = 8
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -51,6 +51,7 @@ class Outputs(C.Structure):
         ("power", C.c_void_p), ("power_stride", C.c_int64),
         ("t_pp", C.c_void_p), ("t_ps", C.c_void_p), ("t_sp", C.c_void_p), ("t_ss", C.c_void_p),
         ("t_mode", C.c_void_p), ("t_mode_stride", C.c_int64),
+        ("power_states", C.c_int32),
     ]
 
 

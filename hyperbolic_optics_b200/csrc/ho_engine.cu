@@ -43,6 +43,7 @@ template <typename T> struct OutPtrs {
   T* power; int64_t power_stride;
   ho::cx<T>* t_pp; ho::cx<T>* t_ps; ho::cx<T>* t_sp; ho::cx<T>* t_ss;
   T* t_mode; int64_t t_mode_stride;
+  int power_states;  // 2: p, s; 4: + (p + s)/sqrt2, (p + i s)/sqrt2
 };
 
 template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p) {
@@ -173,10 +174,9 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
   const T inv_sinc = T(2) * inv_nc;  // 1 / S_z^inc, S_z^inc = n cos(theta) / 2
   const int n_planes = P.n_layers + 1;
   const bool want_power = out.power != nullptr;
-#pragma unroll
-  for (int pol = 0; pol < 2; ++pol) {
+  // one incident state: walk its coordinates (a0, a1) down the stack, evaluating the flux forms
+  auto walk = [&](int pol, cx<T> a0, cx<T> a1) {
     T* dst = out.power + (int64_t)pol * n_planes * out.power_stride + o;
-    cx<T> a0 = c0[pol], a1 = c1[pol];
     T prev = flux_eval(hf[0], a0, a1);
     if (want_power) st_stream(dst, T(1) - prev * inv_sinc);
 #pragma unroll 1
@@ -191,7 +191,7 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
       prev = cur;
     }
     if (want_power) st_stream(dst + out.power_stride, prev * inv_sinc);
-    if (out.t_pp) {
+    if (out.t_pp && pol < 2) {
       // (a0, a1): coordinates at the exit in the kernel basis.  Thickness-sweep kernel, stable
       // recursion: the maps below the swept layer were folded into the parked data (lower[-8..-1]).
       cx<T> e0 = fma(binv[1], a1, binv[0] * a0), e1 = fma(binv[3], a1, binv[2] * a0);
@@ -209,6 +209,19 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
         st_stream(tm, flux_eval(hx, i00 * e0, i10 * e0) * inv_sinc);
         st_stream(tm + out.t_mode_stride, flux_eval(hx, i01 * e1, i11 * e1) * inv_sinc);
       }
+    }
+  };
+#pragma unroll
+  for (int pol = 0; pol < 2; ++pol) walk(pol, c0[pol], c1[pol]);
+  if (want_power && out.power_states == 4) {
+    // mixed Jones states (a_p, a_s) = (1, 1)/sqrt2 and (1, i)/sqrt2: coordinates are linear in the
+    // incident amplitudes; with p and s they determine the flux forms of any incident state
+    const T rs = T(0.70710678118654752440);
+#pragma unroll 1
+    for (int pol = 2; pol < 4; ++pol) {
+      const cx<T> s0 = pol == 2 ? c0[1] : mk<T>(-c0[1].im, c0[1].re);  // a_s = 1 or i
+      const cx<T> s1 = pol == 2 ? c1[1] : mk<T>(-c1[1].im, c1[1].re);
+      walk(pol, rs * (c0[0] + s0), rs * (c1[0] + s1));
     }
   }
 }
@@ -686,6 +699,9 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
     return fail(HO_ERR_BAD_ARGUMENT, "t_pp, t_ps, t_sp, t_ss must be given together");
   o.t_mode = out->t_mode;
   o.t_mode_stride = out->t_mode_stride;
+  o.power_states = out->power_states == 4 ? 4 : 2;
+  if (out->power_states != 0 && out->power_states != 2 && out->power_states != 4)
+    return fail(HO_ERR_BAD_ARGUMENT, "power_states must be 0, 2 or 4");
   if (o.t_mode && !o.t_pp) return fail(HO_ERR_BAD_ARGUMENT, "t_mode needs the t_pp .. t_ss outputs");
   if (o.t_mode && o.t_mode_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "t_mode_stride is smaller than the point range");
   if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
@@ -711,6 +727,7 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.t_pp = o.t_ps = o.t_sp = o.t_ss = nullptr;
   o.t_mode = nullptr;
   o.t_mode_stride = 0;
+  o.power_states = 2;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, n_begin, n_end, s)
                                                    : launch<float, false>(problem, o, n_begin, n_end, s);

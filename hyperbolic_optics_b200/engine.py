@@ -120,7 +120,8 @@ class DeviceOutputs:
         self.mueller = torch.empty((n, 4, 4), dtype=real, device=device) if mueller else None
         self.stokes = torch.empty((n, 4), dtype=real, device=device) if stokes is not None else None
         self.incident_stokes = stokes
-        # power bookkeeping planes [2 * (n_layers + 1)][n]: per polarisation R, T, A_0 .. A_{L-2}
+        # power bookkeeping planes [states * (n_layers + 1)][n]: per incident state R, T, A_0 .. A_{L-2};
+        # states = 2 (p, s) or 4 (+ the two mixed states that determine any Jones state)
         self.power = torch.empty((power_planes, n), dtype=real, device=device) if power_planes else None
         self.t = torch.empty((4, n), dtype=dtype, device=device) if transmission else None  # rows: pp, ps, sp, ss
         # mode-resolved transmittance planes: (p inc, s-like mode), (p, p-like), (s, s-like), (s, p-like)
@@ -155,9 +156,11 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
             if out.incident_stokes is not None:
                 o.incident_stokes = (C.c_double * 4)(*[float(x) for x in out.incident_stokes])
         if out.power is not None and select != "no-power":
-            if out.power.shape[0] != 2 * (len(problem.plan.layers) + 1):
-                raise ValueError("power buffer must have 2 * (n_layers + 1) planes")
+            per = len(problem.plan.layers) + 1
+            if out.power.shape[0] not in (2 * per, 4 * per):
+                raise ValueError("power buffer must have 2 or 4 times (n_layers + 1) planes")
             o.power, o.power_stride = out.power.data_ptr(), out.power.shape[1]
+            o.power_states = out.power.shape[0] // per
         if out.t is not None and select != "power":
             o.t_pp, o.t_ps, o.t_sp, o.t_ss = (out.t[i].data_ptr() for i in range(4))
             o.t_mode, o.t_mode_stride = out.t_mode.data_ptr(), out.t_mode.shape[1]

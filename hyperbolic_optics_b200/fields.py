@@ -1,7 +1,8 @@
 """``FieldProfile`` -- power bookkeeping consumer of an executed ``Structure``.
 
 Mirrors the power half of the reference's ``FieldProfile`` (``fields.py:181-282``):
-``reflectance``, ``transmittance``, ``layer_absorption``, ``summary``, ``check_conservation``.
+``reflectance``, ``transmittance``, ``layer_absorption``, ``summary``, ``check_conservation`` for
+``"p"``, ``"s"`` or a complex ``(a_s, a_p)`` Jones pair.
 The fluxes themselves come out of the fused kernel (``Structure.execute(..., power=True)``):
 per interface a Hermitian 2x2 flux form of ``S_z = 1/2 Re(Ex Hy* - Ey Hx*)`` is kept in
 registers/local memory and evaluated for unit p and s incidence, so -- unlike the reference,
@@ -43,9 +44,34 @@ class FieldProfile:
         self.n_layers = len(self.layers)
 
     def _block(self, polarization):
-        if not isinstance(polarization, str) or polarization.lower() not in ("p", "s"):
-            raise ValueError(f"Unknown polarization {polarization!r}; the GPU power block holds 'p' and 's'.")
-        return self.structure.power[polarization.lower()]
+        """R, T, A_i for ``"p"``, ``"s"`` or a complex ``(a_s, a_p)`` Jones pair
+        (``fields.py:102-118``).  Interface fluxes are Hermitian forms in the incident amplitudes:
+        with F any of 1 - R, T, A_i,
+            F(a) = (|a_p|^2 F_p + |a_s|^2 F_s + 2 Re(conj(a_p) a_s X)) / (|a_p|^2 + |a_s|^2),
+        and X follows from the two mixed states the kernel also evaluates (``power="full"``):
+        Re X = F_d - (F_p + F_s)/2, Im X = (F_p + F_s)/2 - F_c."""
+        if isinstance(polarization, str):
+            key = polarization.lower()
+            if key not in ("p", "s"):
+                raise ValueError(f"Unknown polarization {polarization!r}; use 'p', 's' or an (a_s, a_p) pair.")
+            return self.structure.power[key]
+        a_s, a_p = (complex(x) for x in polarization)
+        norm = abs(a_s) ** 2 + abs(a_p) ** 2
+        if not norm > 0:
+            raise ValueError("the Jones pair (a_s, a_p) must not vanish")
+        self.structure.ensure_full_power()
+        blk = self.structure.power
+        wp, ws = abs(a_p) ** 2 / norm, abs(a_s) ** 2 / norm
+        wx = 2.0 * (a_p.conjugate() * a_s) / norm
+
+        def mix(pick, complement=False):
+            f = [1.0 - pick(blk[k]) if complement else pick(blk[k]) for k in "psdc"]   # flux-linear quantities
+            half = 0.5 * (f[0] + f[1])
+            val = wp * f[0] + ws * f[1] + wx.real * (f[2] - half) - wx.imag * (half - f[3])
+            return 1.0 - val if complement else val
+
+        return {"R": mix(lambda b: b["R"], complement=True), "T": mix(lambda b: b["T"]),
+                "A": [mix(lambda b, i=i: b["A"][i]) for i in range(len(blk["p"]["A"]))]}
 
     def reflectance(self, polarization="p"):
         return self._block(polarization)["R"]

@@ -71,6 +71,7 @@ class Structure:
         self.chunk_points = int(chunk_points)
         self.with_mueller = True
         self.with_power = False
+        self.power_states = 2   # 4: additionally two mixed Jones states (execute(..., power="full"))
         self.with_transmission = False
         self.power = None
         self.incident_stokes = None
@@ -132,6 +133,15 @@ class Structure:
             self.with_transmission = True
             self._run(self._last_backend)
 
+    def ensure_full_power(self):
+        """Power block for all four incident states (any Jones pair can then be evaluated); one
+        re-launch on the kept plan if the structure was executed with ``power=True`` only."""
+        if self.plan is None:
+            raise ValueError("Structure has not been executed; call structure.execute(payload).")
+        if self.power is None or "d" not in self.power:
+            self.with_power, self.power_states = True, 4
+            self._run(self._last_backend)
+
     # -- one-call protocol ---------------------------------------------------------------
     def execute(self, payload, backend="transfer", mueller=True, incident_stokes=None,
                 keep_on_device=False, own_results=None, power=False, transmission=False, shard=None,
@@ -140,6 +150,7 @@ class Structure:
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
         self.with_mueller = bool(mueller)
         self.with_power = bool(power)
+        self.power_states = 4 if power == "full" else 2
         self.with_transmission = bool(transmission)
         self.incident_stokes = incident_stokes
         self.keep_on_device = bool(keep_on_device)
@@ -189,7 +200,7 @@ class Structure:
         if n == 0:
             raise ValueError(f"shard {self.shard}: more ranks than samples of the sharded axis")
         want_stokes = self.incident_stokes is not None
-        planes = 2 * (len(plan.layers) + 1) if self.with_power else 0
+        planes = self.power_states * (len(plan.layers) + 1) if self.with_power else 0
         cdtype = torch.complex64 if self.precision == "complex64" else torch.complex128
         rdtype = torch.float32 if self.precision == "complex64" else torch.float64
         if self.keep_on_device:
@@ -267,10 +278,11 @@ class Structure:
             self.mode_transmittance = {"p": {"s": tm[0], "p": tm[1]}, "s": {"s": tm[2], "p": tm[3]}}
         self.power = None
         if power is not None:
-            # planes per polarisation: R, T, A_0 .. A_{L-2}  (include/ho_b200.h, ho_outputs_t.power)
-            per = power.shape[0] // 2
+            # planes per incident state: R, T, A_0 .. A_{L-2}  (include/ho_b200.h, ho_outputs_t.power);
+            # "d" = (a_p, a_s) = (1, 1)/sqrt2 and "c" = (1, i)/sqrt2 only with power="full"
+            per = len(self.plan.layers) + 1
             self.power = {}
-            for pi, pol in enumerate("ps"):
+            for pi, pol in enumerate("psdc"[:power.shape[0] // per]):
                 blk = [pres(conv(power[pi * per + k].reshape(shape))) for k in range(per)]
                 self.power[pol] = {"R": blk[0], "T": blk[1], "A": blk[2:]}
 

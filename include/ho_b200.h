@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 7
+#define HO_ABI_VERSION 8
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -130,6 +130,11 @@ typedef struct {
      FieldProfile.polarization_resolved (fields.py:286-356; its T_co / T_cross).  NULL to skip. */
   double* t_mode;
   int64_t t_mode_stride; /* >= n_end - n_begin */
+  /* Number of incident states of the power block: 0 or 2 = p and s (above); 4 = additionally the
+     states (a_p, a_s) = (1, 1)/sqrt2 and (1, i)/sqrt2 in planes 2*(n_layers+1) .. 4*(n_layers+1)-1.
+     Fluxes are Hermitian forms in (a_p, a_s), so these four determine R, T, A_i of ANY Jones
+     state (fields.py:102-118 accepts a complex (a_s, a_p) pair). */
+  int32_t power_states;
 } ho_outputs_t;
 
 /* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /

@@ -555,7 +555,10 @@ def _sz(field):
 
 def power_summary(layers, gamma, polarization="p"):
     """R, T, per-layer absorption from interface fluxes   (fields.py:120-282)."""
-    a_s, a_p = (0j, 1 + 0j) if polarization == "p" else (1 + 0j, 0j)
+    if isinstance(polarization, str):   # fields.py:102-118
+        a_s, a_p = (0j, 1 + 0j) if polarization == "p" else (1 + 0j, 0j)
+    else:
+        a_s, a_p = (complex(x) for x in polarization)
     m2 = np.stack([np.stack([gamma[..., 0, 0], gamma[..., 0, 2]], -1),
                    np.stack([gamma[..., 2, 0], gamma[..., 2, 2]], -1)], -2)
     rhs = np.broadcast_to(np.array([a_s, a_p], dtype=np.complex128), m2.shape[:-2] + (2,))[..., None]

@@ -39,7 +39,7 @@ from hyperbolic_optics.mueller import Mueller  # noqa: E402  (reference)
 from tests.golden.make_fixtures import run_reference, sample, strides_for  # noqa: E402
 from tests.golden.payloads import ALL, angle_overrides  # noqa: E402
 
-from tests.golden.make_polarimetry_golden_spec import JONES_CHAIN, MUELLER_CHAINS, NAMES  # noqa: E402
+from tests.golden.make_polarimetry_golden_spec import JONES_CHAIN, JONES_PAIR, MUELLER_CHAINS, NAMES  # noqa: E402
 
 
 def build(name):
@@ -91,6 +91,9 @@ def build(name):
             for key, val in fp.polarization_resolved(pol).items():
                 out[f"pr_{pol}_{key}"] = sample(val, strides)
             out[f"pr_{pol}_T"] = sample(fp.transmittance(pol), strides)
+        summ = fp.summary(JONES_PAIR)          # arbitrary (a_s, a_p) incident state, fields.py:102-118
+        out["pair_R"], out["pair_T"] = sample(summ["R"], strides), sample(summ["T"], strides)
+        out["pair_A_total"] = sample(summ["total_absorption"], strides)
         ep = Jones(st).find_exceptional_points(0.9)
         out["ep_near"] = sample(ep["near_ep"], strides)
         out["ep_index"] = np.array(ep["ep_index"], dtype=np.int64)

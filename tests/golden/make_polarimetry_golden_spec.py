@@ -12,3 +12,5 @@ MUELLER_CHAINS = {
 }
 JONES_CHAIN = (("elliptical", {"alpha": 30, "ellipticity": 20}),
                [("quarter_wave_plate", 15), ("sample",), ("rotator", 12), ("linear_polarizer", 60)])
+# (a_s, a_p) of the arbitrary incident state used for FieldProfile.summary
+JONES_PAIR = (0.6 - 0.3j, 0.2 + 0.7j)

@@ -444,3 +444,45 @@ def test_polarization_resolved(name, backend, built_library):
         for pol in "ps":
             res = fp.polarization_resolved(pol)
             assert np.abs(np.asarray(res["T_co"]) + np.asarray(res["T_cross"]) - np.asarray(fp.transmittance(pol))).max() <= 1e-10
+
+
+@pytest.mark.parametrize("backend", ["transfer", "scattering"])
+@pytest.mark.parametrize("name", ["simple_calcite", "incident_calcite", "fullsweep_quartz", "dispersion_iso_exit",
+                                  "multilayer_incident"])
+def test_power_for_arbitrary_jones_state(name, backend, built_library):
+    """FieldProfile with a complex (a_s, a_p) pair (reference fields.py:102-118): R, T and the total
+    absorption from the four-state power block vs the reference's values; conservation."""
+    from hyperbolic_optics_b200 import FieldProfile
+    from tests.golden.make_polarimetry_golden_spec import JONES_PAIR
+
+    fx = load(name)
+    s = _run_gpu(name, backend, with_power=True)
+    assert set(s.power) == {"p", "s"}
+    fp = FieldProfile(s)
+    summ = fp.summary(JONES_PAIR)              # triggers the four-state re-launch
+    assert set(s.power) == {"p", "s", "d", "c"}
+    strides = fx["strides"]
+    ok = np.isfinite(fx["pair_R"]) & np.isfinite(fx["pair_T"]) & (np.abs(fx["pair_R"] + fx["pair_T"] + fx["pair_A_total"] - 1) <= 1e-9)
+    ok &= np.abs(fx["pr_p_R_co"] - np.abs(fx["r_pp"]) ** 2) <= 1e-9   # reference self-consistency (thick stacks)
+    assert ok.mean() > 0.7
+    for key, ref in (("R", "pair_R"), ("T", "pair_T"), ("total_absorption", "pair_A_total")):
+        err = np.abs(_sampled(summ[key], strides) - fx[ref])[ok]
+        assert err.max() <= 1e-9, f"{name}/{backend}/{key}: {err.max():.2e}"
+    assert summ["conservation_residual"] <= 1e-9 or backend == "transfer"
+    # pure states through the tuple interface equal the string interface
+    for pol, pair in (("p", (0.0, 1.0)), ("s", (1.0, 0.0))):
+        a, b = np.asarray(fp.reflectance(pair)), np.asarray(fp.reflectance(pol))
+        fin = np.isfinite(a) & np.isfinite(b)
+        assert np.abs(a - b)[fin].max() <= 1e-12
+    with pytest.raises(ValueError):
+        fp.reflectance((0.0, 0.0))
+    # execute(..., power="full") fills the four states in the first launch
+    from hyperbolic_optics_b200 import Structure
+    from tests.golden.payloads import ALL as PAYLOADS
+    if not any(x is not None for x in angle_overrides(PAYLOADS[name])):
+        s2 = Structure(device="cuda:0")
+        s2.execute(PAYLOADS[name]["payload"], backend=backend, power="full")
+        assert set(s2.power) == {"p", "s", "d", "c"}
+        a, b = np.asarray(FieldProfile(s2).transmittance(JONES_PAIR)), np.asarray(summ["T"])
+        fin = np.isfinite(a) & np.isfinite(b)
+        assert np.abs(a - b)[fin].max() <= 1e-12
