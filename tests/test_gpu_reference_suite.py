@@ -207,3 +207,67 @@ def test_large_incident_array_and_dispersion_stability(api):
     assert s.r_pp.shape == (410, 4096) and np.isfinite(s.r_pp).all()
     d = run(api, DISPERSION, "scattering")
     assert np.isfinite(d.r_pp).all() and np.isfinite(d.r_ss).all()
+
+
+# ---- tests/test_polarization.py of the reference: cross-polarisation tools ----
+
+POL_SIMPLE = {"type": "Simple", "incidentAngle": 20.0, "azimuthal_angle": 0.0, "frequency": 1460.0}
+
+
+def converting_stack(eps_prism=25.0, eps_exit=1.0):
+    """A calcite film rotated in-plane: genuine s <-> p conversion (test_polarization.py:27-41)."""
+    return [{"type": "Ambient Incident Layer", "permittivity": eps_prism},
+            {"type": "Isotropic Middle-Stack Layer", "thickness": 0.5, "permittivity": 1.0},
+            {"type": "Crystal Layer", "material": "Calcite", "thickness": 1.0, "rotationY": 90, "rotationZ": 30},
+            {"type": "Semi Infinite Isotropic Layer", "permittivity": eps_exit}]
+
+
+def test_polarization_resolved_reflection_and_conservation(api):
+    s = run(api, {"ScenarioData": POL_SIMPLE, "Layers": converting_stack()}, power=True)
+    fp = api.FieldProfile(s)
+    res = fp.polarization_resolved("p")
+    assert res["R_co"] == pytest.approx(abs(complex(s.r_pp)) ** 2, abs=1e-9)
+    assert res["R_cross"] == pytest.approx(abs(complex(s.r_ps)) ** 2, abs=1e-9)
+    assert float(res["R_cross"]) > 1e-6                      # an in-plane rotated film converts p into s
+    assert 0.0 <= float(res["conversion_reflection"]) <= 1.0
+    absorbed = float(fp.summary("p")["total_absorption"])
+    total = sum(float(res[k]) for k in ("R_co", "R_cross", "T_co", "T_cross")) + absorbed
+    assert total == pytest.approx(1.0, abs=1e-9)           # isotropic exit: the s / p split is exact
+    assert float(res["R_co"]) + float(res["R_cross"]) == pytest.approx(float(fp.reflectance("p")), abs=1e-9)
+    assert float(res["T_co"]) + float(res["T_cross"]) == pytest.approx(float(fp.transmittance("p")), abs=1e-9)
+    with pytest.raises(ValueError):
+        fp.polarization_resolved((1.0, 1.0))
+
+
+def test_transmission_mueller_matrix(api):
+    s = run(api, {"ScenarioData": POL_SIMPLE, "Layers": converting_stack()}, power=True)
+    m = api.Mueller(s).calculate_transmission_mueller_matrix()
+    assert m.shape == (4, 4) and np.isrealobj(m)
+    # symmetric system (prism eps == exit eps): |t|^2 is power, so M_t[0, 0] is the unpolarised flux T
+    sym = run(api, {"ScenarioData": POL_SIMPLE, "Layers": converting_stack(eps_prism=2.0, eps_exit=2.0)}, power=True)
+    mt = api.Mueller(sym).calculate_transmission_mueller_matrix()
+    fp = api.FieldProfile(sym)
+    assert float(mt[0, 0]) == pytest.approx(0.5 * (float(fp.transmittance("p")) + float(fp.transmittance("s"))), abs=1e-9)
+    # the shared Jones -> Mueller map reproduces the fused reflection Mueller matrix
+    mu = api.Mueller(s)
+    mu.calculate_mueller_matrix()
+    direct = mu._mueller_from_jones(s.r_pp, s.r_ps, s.r_sp, s.r_ss)
+    assert np.allclose(mu.mueller_matrix, direct, atol=1e-13, rtol=0)
+
+
+def test_mixed_jones_state_power(api):
+    """FieldProfile with an (a_s, a_p) pair (fields.py:102-118): diagonal linear light on the
+    converting stack conserves energy and lies between the pure states only on average."""
+    s = run(api, {"ScenarioData": POL_SIMPLE, "Layers": converting_stack()}, power=True)
+    fp = api.FieldProfile(s)
+    pair = (1.0 / np.sqrt(2.0), 1.0 / np.sqrt(2.0))
+    summ = fp.summary(pair)
+    assert summ["conservation_residual"] <= 1e-9
+    # unpolarised average: the cross terms of +45 and -45 degree light cancel
+    anti = fp.summary((1.0 / np.sqrt(2.0), -1.0 / np.sqrt(2.0)))
+    mean_rt = 0.5 * (float(summ["R"]) + float(anti["R"]))
+    assert mean_rt == pytest.approx(0.5 * (float(fp.reflectance("p")) + float(fp.reflectance("s"))), abs=1e-12)
+    # R of a mixed state from the amplitude coefficients: |r_pp a_p + r_sp a_s|^2 + |r_ps a_p + r_ss a_s|^2
+    a_s, a_p = pair
+    refl = abs(s.r_pp * a_p + s.r_sp * a_s) ** 2 + abs(s.r_ps * a_p + s.r_ss * a_s) ** 2
+    assert float(summ["R"]) == pytest.approx(float(refl), abs=1e-9)
