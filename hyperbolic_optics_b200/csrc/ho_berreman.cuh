@@ -555,20 +555,23 @@ template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs
   if (!(norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1)))) return false;
   cx<T> idy = recip(dy);
   cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
-#pragma unroll
-  for (int it = 0; it < 3; ++it) {
+  // two steps; a third only where the second still moved (rate ~ tilt |mu| / |y0 - y1|: step k has
+  // size rate^k, the error after it rate^(k+1))
+  bool done = false;
+#pragma unroll 1
+  for (int it = 0; it < 3 && !done; ++it) {
     b1 = c3 - u;
     b0 = c2 - v - u * b1;
     du = (c1 - u * b0 - v * b1) * idy;
     dv = (c0 - v * b0) * idy;
     u = u + du;
     v = v + dv;
+    T nv = norm2(v), ndu = norm2(du);
+    done = it >= 1 && norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv;  // |du|^2 <= tol |v|
   }
+  if (!done) return false;
   b1 = c3 - u;
   b0 = c2 - v - u * b1;
-  T nv = norm2(v);
-  T ndu = norm2(du);
-  if (!(norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv)) return false;  // |du|^2 <= tol |v|
   Spectrum<T> s;
   s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   // pair 0

@@ -724,17 +724,21 @@ def pair_symmetric_split(c3, c2, c1, c0, iters=3):
     dy = y0 - y1
     idy = 1.0 / np.where(dy == 0, 1.0, dy)
     u, v = np.zeros_like(y0), -y0
-    for _ in range(iters):
+    done = np.zeros(np.shape(y0), dtype=bool)
+    for it in range(iters):   # two steps; a third only where the second still moved
         b1 = c3 - u
         b0 = c2 - v - u * b1
         du, dv = (c1 - u * b0 - v * b1) * idy, (c0 - v * b0) * idy
-        u, v = u + du, v + dv
+        u, v = np.where(done, u, u + du), np.where(done, v, v + dv)
+        if it >= 1:
+            done = done | ((np.abs(dv) ** 2 <= PAIR_STEP * np.abs(v) ** 2)
+                           & (np.abs(du) ** 4 <= PAIR_STEP ** 2 * np.abs(v) ** 2))
     b1 = c3 - u
     b0 = c2 - v - u * b1
     n2 = np.abs(c2) ** 2
     ok = (np.abs(c3) ** 4 <= PAIR_ODD * n2) & (np.abs(c1) ** 4 <= PAIR_ODD * n2 ** 3)
     ok &= np.abs(dy) ** 2 >= PAIR_SEPARATION * (np.abs(y0) ** 2 + np.abs(y1) ** 2)
-    ok &= np.abs(du) ** 2 * np.abs(v) + np.abs(dv) ** 2 <= PAIR_STEP * np.abs(v) ** 2
+    ok &= done
     return u, v, b1, b0, ok
 
 
