@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 8
+HO_ABI_VERSION = 9
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -76,7 +76,22 @@ class Polarimetry(C.Structure):
     ]
 
 
-EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_measure_fp64_peak", "ho_launch_count",
+HO_MAX_OSC = 8
+HO_MAT_TOLO, HO_MAT_MONOCLINIC = 1, 2
+
+
+class MaterialDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_osc", C.c_int32 * 3),
+        ("eps_inf", C.c_double * 4),
+        ("w_to", (C.c_double * HO_MAX_OSC) * 3), ("g_to", (C.c_double * HO_MAX_OSC) * 3),
+        ("w_lo", (C.c_double * HO_MAX_OSC) * 3), ("g_lo", (C.c_double * HO_MAX_OSC) * 3),
+        ("amp", (C.c_double * HO_MAX_OSC) * 2), ("alpha", C.c_double * HO_MAX_OSC),
+        ("rot", C.c_double * 9),
+    ]
+
+
+EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_material_table", "ho_measure_fp64_peak", "ho_launch_count",
            "ho_abi_version", "ho_last_error")
 
 
@@ -98,6 +113,8 @@ def load():
     lib.ho_reflect_f32.restype = C.c_int
     lib.ho_polarimetry.argtypes = [C.POINTER(Polarimetry), C.c_int64, C.c_void_p]
     lib.ho_polarimetry.restype = C.c_int
+    lib.ho_material_table.argtypes = [C.POINTER(MaterialDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.ho_material_table.restype = C.c_int
     lib.ho_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
     lib.ho_measure_fp64_peak.restype = C.c_int
     lib.ho_launch_count.argtypes = []

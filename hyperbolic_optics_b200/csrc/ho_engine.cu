@@ -779,6 +779,20 @@ int ho_polarimetry(const ho_polarimetry_t* q, int64_t n, void* cuda_stream) {
   return HO_OK;
 }
 
+int ho_material_table(const ho_material_t* m, const double* freq, int64_t F, ho_c128* eps_out, void* cuda_stream) {
+  if (!m || !freq || !eps_out || F < 0) return fail(HO_ERR_BAD_ARGUMENT, "ho_material_table: null argument or negative F%s");
+  if (m->kind != HO_MAT_TOLO && m->kind != HO_MAT_MONOCLINIC) return fail(HO_ERR_BAD_ARGUMENT, "ho_material_table: unknown material kind%s");
+  for (int a = 0; a < 3; ++a)
+    if (m->n_osc[a] < 0 || m->n_osc[a] > HO_MAX_OSC) return fail(HO_ERR_BAD_ARGUMENT, "ho_material_table: more than HO_MAX_OSC oscillators%s");
+  if (F == 0) return HO_OK;
+  const int64_t want = (F + 127) / 128;
+  material_table_kernel<<<(int)(want < 4096 ? want : 4096), 128, 0, (cudaStream_t)cuda_stream>>>(*m, freq, F, eps_out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_material_table launch: %s", cudaGetErrorString(err));
+  g_launches.fetch_add(1);
+  return HO_OK;
+}
+
 int64_t ho_launch_count(void) { return g_launches.load(); }
 int ho_abi_version(void) { return HO_ABI_VERSION; }
 const char* ho_last_error(void) { return g_error; }

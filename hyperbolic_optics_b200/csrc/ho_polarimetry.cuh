@@ -284,4 +284,58 @@ polarimetry_kernel(const __grid_constant__ ho_polarimetry_t q, int64_t n) {
   }
 }
 
+// eps(f) of a built-in dispersion model, rotated by Q = Ry*Rx, packed symmetric
+__global__ void __launch_bounds__(128)
+material_table_kernel(const __grid_constant__ ho_material_t m, const double* __restrict__ freq, int64_t F, ho_c128* __restrict__ out) {
+  using namespace ho;
+  typedef cx<double> C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < F; i += (int64_t)gridDim.x * blockDim.x) {
+    const double f = freq[i], f2 = f * f;
+    C e[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) e[r][c] = mk<double>(0.0, 0.0);
+    if (m.kind == HO_MAT_TOLO) {
+      // eps_inf * prod_k (w_lo^2 - f^2 - i f g_lo) / (w_to^2 - f^2 - i f g_to)   (materials.py:176-213)
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        C prod = mk<double>(1.0, 0.0);
+        for (int k = 0; k < m.n_osc[ax]; ++k) {
+          const C num = mk<double>(m.w_lo[ax][k] * m.w_lo[ax][k] - f2, -f * m.g_lo[ax][k]);
+          const C den = mk<double>(m.w_to[ax][k] * m.w_to[ax][k] - f2, -f * m.g_to[ax][k]);
+          prod = prod * (num / den);
+        }
+        e[ax][ax] = m.eps_inf[ax] * prod;
+      }
+    } else {
+      // monoclinic: Bu modes in the x-y plane at angles alpha, Au modes along z (materials.py:614-651)
+      C xx = mk<double>(m.eps_inf[0], 0.0), yy = mk<double>(m.eps_inf[1], 0.0), xy = mk<double>(m.eps_inf[2], 0.0);
+      C zz = mk<double>(m.eps_inf[3], 0.0);
+      for (int k = 0; k < m.n_osc[0]; ++k) {
+        const C rho = (m.amp[0][k] * m.amp[0][k]) * recip(mk<double>(m.w_to[0][k] * m.w_to[0][k] - f2, -f * m.g_to[0][k]));
+        double sa, ca;
+        sincos(m.alpha[k], &sa, &ca);
+        xx = xx + (ca * ca) * rho; xy = xy + (sa * ca) * rho; yy = yy + (sa * sa) * rho;
+      }
+      for (int k = 0; k < m.n_osc[1]; ++k)
+        zz = zz + (m.amp[1][k] * m.amp[1][k]) * recip(mk<double>(m.w_to[1][k] * m.w_to[1][k] - f2, -f * m.g_to[1][k]));
+      e[0][0] = xx; e[0][1] = xy; e[1][0] = xy; e[1][1] = yy; e[2][2] = zz;
+    }
+    // (Q e) Q^T, Q real
+    C t[3][3], r[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) t[a][b] = m.rot[3 * a] * e[0][b] + m.rot[3 * a + 1] * e[1][b] + m.rot[3 * a + 2] * e[2][b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) r[a][b] = t[a][0] * m.rot[3 * b] + t[a][1] * m.rot[3 * b + 1] + t[a][2] * m.rot[3 * b + 2];
+    ho_c128* o = out + 6 * i;
+    st_plain(o + 0, r[0][0]); st_plain(o + 1, r[0][1]); st_plain(o + 2, r[0][2]);
+    st_plain(o + 3, r[1][1]); st_plain(o + 4, r[1][2]); st_plain(o + 5, r[2][2]);
+  }
+}
+
 }  // namespace

@@ -28,7 +28,7 @@ def _require_cuda(device):
 class DeviceProblem:
     """A ``StackPlan`` resident on one GPU plus the filled ``ho_problem_t`` descriptor."""
 
-    def __init__(self, plan: P.StackPlan, backend="transfer", device=None):
+    def __init__(self, plan: P.StackPlan, backend="transfer", device=None, device_tables=False):
         if backend not in BACKENDS:
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
         if len(plan.layers) > nat.HO_MAX_LAYERS:
@@ -82,6 +82,53 @@ class DeviceProblem:
         for i, name, slot in layer_slots:
             setattr(d.layers[i], name, addr(slot))
         self.desc = d
+        self.device_table_layers = []
+        if device_tables:
+            self._fill_tables_on_device(layer_slots, addr)
+
+    def _fill_tables_on_device(self, layer_slots, addr):
+        """eps(f) of the built-in dispersion models evaluated and rotated by
+        ``ho_material_table`` straight into the arena slots the layer descriptors point at (the
+        host values uploaded above are overwritten; they stay the reference for the tests)."""
+        plan = self.plan
+        freq = np.atleast_1d(np.asarray(plan.frequency, dtype=np.float64))
+        self._freq_dev = torch.from_numpy(np.ascontiguousarray(freq)).to(self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        eps_slot = {i: slot for i, name, slot in layer_slots if name == "eps"}
+        for i, lp in enumerate(plan.layers):
+            mat = lp.material
+            if mat is None or mat.kind not in ("tolo", "mono") or lp.eps.shape[0] != freq.size or freq.size < 2:
+                continue
+            m = nat.MaterialDesc()
+            if mat.kind == "tolo":
+                m.kind = nat.HO_MAT_TOLO
+                axes = [mat.params[k] for k in (("o", "o", "e") if "o" in mat.params else ("x", "y", "z"))]
+                if any(len(ax["w_to"]) > nat.HO_MAX_OSC for ax in axes):
+                    continue   # more oscillators than the descriptor holds: keep the host table
+                for a, ax in enumerate(axes):
+                    m.n_osc[a] = len(ax["w_to"])
+                    m.eps_inf[a] = float(ax["eps_inf"])
+                    for k in range(m.n_osc[a]):
+                        m.w_to[a][k], m.g_to[a][k] = float(ax["w_to"][k]), float(ax["g_to"][k])
+                        m.w_lo[a][k], m.g_lo[a][k] = float(ax["w_lo"][k]), float(ax["g_lo"][k])
+            else:
+                m.kind = nat.HO_MAT_MONOCLINIC
+                bu, au = mat.params["bu"], mat.params["au"]
+                if len(bu["w_to"]) > nat.HO_MAX_OSC or len(au["w_to"]) > nat.HO_MAX_OSC:
+                    continue
+                m.n_osc[0], m.n_osc[1] = len(bu["w_to"]), len(au["w_to"])
+                m.eps_inf[0], m.eps_inf[1] = float(bu["eps_inf"]["xx"]), float(bu["eps_inf"]["yy"])
+                m.eps_inf[2], m.eps_inf[3] = float(bu["eps_inf"]["xy"]), float(au["eps_inf"])
+                for k in range(m.n_osc[0]):
+                    m.w_to[0][k], m.g_to[0][k], m.amp[0][k] = float(bu["w_to"][k]), float(bu["g_to"][k]), float(bu["amp"][k])
+                    m.alpha[k] = float(bu["alpha_deg"][k]) * np.pi / 180.0
+                for k in range(m.n_osc[1]):
+                    m.w_to[1][k], m.g_to[1][k], m.amp[1][k] = float(au["w_to"][k]), float(au["g_to"][k]), float(au["amp"][k])
+            q = np.asarray(lp.rotation_xy if lp.rotation_xy is not None else np.eye(3), dtype=np.float64)
+            m.rot = (C.c_double * 9)(*q.reshape(9))
+            nat.check(nat.lib().ho_material_table(C.byref(m), self._freq_dev.data_ptr(), freq.size,
+                                                  addr(eps_slot[i]), stream))
+            self.device_table_layers.append(i)
 
     def _put_f64(self, arr):
         off = sum(np.size(x) for x in self._f64)

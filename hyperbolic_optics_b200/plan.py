@@ -57,6 +57,7 @@ class LayerPlan:
     exit_n: float = 1.0
     eps_exit: float | None = None
     material: object = None
+    rotation_xy: np.ndarray | None = None  # Ry*Rx of a crystal layer (identity for an isotropic crystal's exact table)
 
 
 @dataclass
@@ -220,6 +221,7 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
             lp.eps, lp.mu, lp.mu_scalar = np.ascontiguousarray(eps), np.ascontiguousarray(mu), mu_scalar
             lp.eps_scalar = eps_scalar
             lp.cos_beta, lp.sin_beta, lp.material = cos_b, sin_b, material
+            lp.rotation_xy = np.eye(3) if eps_scalar else q
         elif kind == TYPE_ISO_EXIT:
             eps_exit = data.get("permittivity")
             if eps_exit is None:

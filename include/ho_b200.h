@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 8
+#define HO_ABI_VERSION 9
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -184,6 +184,28 @@ typedef struct {
                              Mueller matrix, mueller.py:327-356) */
 } ho_polarimetry_t;
 int ho_polarimetry(const ho_polarimetry_t* request, int64_t n, void* cuda_stream);
+
+/* Device-side material tables: eps(f) of a built-in dispersion model evaluated and rotated on the
+   GPU straight into the table a layer descriptor points at, instead of NumPy on the host + H2D
+   (reference materials.py:176-213 TO/LO product per principal axis, :614-651 monoclinic beta-Ga2O3,
+   layers.py:402-417 R eps R^T with the batch-independent Ry*Rx part).  One thread per frequency. */
+enum ho_material_kind { HO_MAT_TOLO = 1, HO_MAT_MONOCLINIC = 2 };
+#define HO_MAX_OSC 8
+typedef struct {
+  int32_t kind;
+  int32_t n_osc[3];            /* TOLO: oscillators of the x, y, z axes; MONOCLINIC: {n_bu, n_au, 0} */
+  double eps_inf[4];           /* TOLO: x, y, z; MONOCLINIC: Bu xx, yy, xy and Au zz */
+  double w_to[3][HO_MAX_OSC];  /* TOLO: per axis; MONOCLINIC: [0] = Bu modes, [1] = Au modes */
+  double g_to[3][HO_MAX_OSC];
+  double w_lo[3][HO_MAX_OSC];  /* TOLO only */
+  double g_lo[3][HO_MAX_OSC];
+  double amp[2][HO_MAX_OSC];   /* MONOCLINIC: [0] = Bu, [1] = Au amplitudes */
+  double alpha[HO_MAX_OSC];    /* MONOCLINIC: Bu mode angles, radians */
+  double rot[9];               /* row-major Q = Ry*Rx; the table holds Q eps Q^T (identity: unrotated) */
+} ho_material_t;
+/* freq: device [F] float64 (cm^-1); eps_out: device [F][6] complex128 (xx, xy, xz, yy, yz, zz) */
+int ho_material_table(const ho_material_t* material, const double* freq, int64_t F, ho_c128* eps_out,
+                      void* cuda_stream);
 
 /* FP64 FMA-chain microbenchmark used as the roofline denominator: runs `iters` dependent
    FMA rounds on every SM and returns achieved FLOP/s (2 flops per FMA) in *flops_per_s. */

@@ -685,3 +685,37 @@ def test_fast_path_protocol_equals_general_kernel(name, built_library, monkeypat
             assert (a[fin] - b[fin]).abs().max().item() <= 1e-12 * max(scale, 1.0)
             ma = res[flag].mueller
             assert (ma[finm] - mb[finm]).abs().max().item() <= 1e-12 * max(mb[finm].abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("material", ["Quartz", "Sapphire", "Calcite", "AlN", "SiC", "hBN", "GaN", "MoO3", "GalliumOxide"])
+def test_device_side_material_tables(material, built_library):
+    """ho_material_table (dispersion model + Ry*Rx rotation on the GPU) reproduces the
+    host tables -- which equal the reference's (tests/test_host.py) -- to a few ulp, and a sweep run
+    from device-built tables equals the run from host-built ones."""
+    from hyperbolic_optics_b200 import Structure, engine
+    from hyperbolic_optics_b200.plan import build_plan
+    from hyperbolic_optics_b200.scenario import ScenarioSetup
+
+    payload = {"ScenarioData": {"type": "Incident"},
+               "Layers": [{"type": "Ambient Incident Layer", "permittivity": 25.0},
+                          {"type": "Crystal Layer", "material": material, "thickness": 0.3, "rotationX": 20, "rotationY": 65,
+                           "rotationZ": 10},
+                          {"type": "Semi Infinite Anisotropic Layer", "material": material, "rotationY": 90}]}
+    plan = build_plan(ScenarioSetup(payload["ScenarioData"], n_incident=64), payload["Layers"])
+    host = engine.DeviceProblem(plan, "transfer", "cuda:0")
+    dev = engine.DeviceProblem(plan, "transfer", "cuda:0", device_tables=True)
+    torch.cuda.synchronize()
+    assert dev.device_table_layers == [0, 1]
+    a, b = dev._c128_dev.cpu().numpy(), host._c128_dev.cpu().numpy()
+    scale = np.abs(b).max()
+    assert np.abs(a - b).max() <= 2e-14 * scale, f"{material}: {np.abs(a - b).max() / scale:.2e}"
+    res = {}
+    for flag in (False, True):
+        s = Structure(device="cuda:0", device_tables=flag)
+        s.execute(payload)
+        res[flag] = np.stack([s.r_pp, s.r_ps, s.r_sp, s.r_ss])
+    fin = np.isfinite(res[False])
+    assert np.array_equal(np.isfinite(res[True]), fin)
+    # a-few-ulp table differences are amplified at ill-conditioned points (TO poles, grazing angles)
+    diff = np.abs(res[True] - res[False])[fin]
+    assert diff.max() <= 1e-9 and np.median(diff) <= 1e-14

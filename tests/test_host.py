@@ -119,7 +119,7 @@ def test_present_squeezes_like_reference():
 def test_library_exports_every_declared_symbol(built_library):
     header = (ROOT / "include" / "ho_b200.h").read_text()
     declared = set(re.findall(r"\b(ho_[a-z0-9_]+)\s*\(", header))
-    assert {"ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_measure_fp64_peak", "ho_launch_count",
+    assert {"ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_material_table", "ho_measure_fp64_peak", "ho_launch_count",
             "ho_abi_version", "ho_last_error"} <= declared
     for sym in declared:
         assert hasattr(built_library, sym), f"{sym} declared in ho_b200.h but not exported"
@@ -145,6 +145,8 @@ def test_descriptor_validation_without_gpu(built_library):
     assert built_library.ho_polarimetry(ctypes.byref(req), 16, None) == -1
     assert b"Jones planes" in built_library.ho_last_error()
     assert built_library.ho_polarimetry(ctypes.byref(req), 0, None) == 0  # empty range: nothing to do
+    mat = nat.MaterialDesc()
+    assert built_library.ho_material_table(ctypes.byref(mat), None, 4, None, None) == -1
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -159,14 +161,16 @@ def test_struct_layout_matches_header(tmp_path):
         'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ho_layer_t), sizeof(ho_problem_t), '
         'offsetof(ho_problem_t, layers), offsetof(ho_layer_t, eps), offsetof(ho_layer_t, exit_n), '
         'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_mode), sizeof(ho_polarimetry_t), '
-        'offsetof(ho_polarimetry_t, j_post), offsetof(ho_polarimetry_t, mueller)); return 0; }\n')
+        'offsetof(ho_polarimetry_t, j_post), offsetof(ho_polarimetry_t, mueller)); '
+        'printf("%zu %zu %zu\\n", sizeof(ho_material_t), offsetof(ho_material_t, amp), offsetof(ho_material_t, rot)); return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [ctypes.sizeof(nat.LayerDesc), ctypes.sizeof(nat.Problem), nat.Problem.layers.offset,
                    nat.LayerDesc.eps.offset, nat.LayerDesc.exit_n.offset, ctypes.sizeof(nat.Outputs),
                    nat.Outputs.t_mode.offset, ctypes.sizeof(nat.Polarimetry), nat.Polarimetry.j_post.offset,
-                   nat.Polarimetry.mueller.offset]
+                   nat.Polarimetry.mueller.offset, ctypes.sizeof(nat.MaterialDesc), nat.MaterialDesc.amp.offset,
+                   nat.MaterialDesc.rot.offset]
 
 
 def test_product_never_imports_oracle():
