@@ -285,6 +285,36 @@ def run_b200_arm(args, rank, local_rank, world):
     checksum = float(torch.view_as_real(out.r).abs().sum().item())
     finite = bool(torch.isfinite(torch.view_as_real(out.r)).all().item())
 
+    # ---- informational: the polarimetry epilogue on the resident r planes (second kernel family) ----
+    epilogue = None
+    if rank == 0:
+        try:
+            from hyperbolic_optics_b200 import polarimetry as pol
+
+            planes = pol.JonesPlanes(out.r[0], out.r[1], out.r[2], out.r[3])
+            s_pre = np.array([1.0, 0.0, 1.0, 0.0])
+            for _ in range(2):
+                pol.run(planes, ("stokes", "polarisation"), s_pre=s_pre)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            p0.record(stream)
+            for _ in range(reps):
+                pol.run(planes, ("stokes", "polarisation"), s_pre=s_pre)
+            p1.record(stream)
+            torch.cuda.synchronize()
+            pms = p0.elapsed_time(p1) / reps
+            gbs = n_local * 120.0 / (pms * 1e-3) / 1e9
+            pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+            hbm_peak_e = pk.get("hbm_gbs", 6650.0)
+            hbm_src_e = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in pk else "fallback (B200_PROFILING.md)"
+            epilogue = {"what": "polarimetry_kernel: Stokes chain + DOP / ellipticity / azimuth of 45-degree linear light "
+                                "from the resident r_ij planes (64 B read + 56 B written per point)",
+                        "points": n_local, "kernel_ms": pms, "points_per_s": n_local / (pms * 1e-3),
+                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_e, "unit": "GB/s",
+                                     "frac": gbs / hbm_peak_e, "peak_source": hbm_src_e}}
+        except Exception as exc:  # informational only: never fail the bench line
+            epilogue = {"error": repr(exc)}
+
     # ---- end to end through the public API with host buffers ("e2e") ----
     # each rank runs its own 410-frequency slab as a stand-alone Structure.execute() call
     lo_f, hi_f = sharding.split_units(f_per * world, world, rank)
@@ -400,6 +430,8 @@ def run_b200_arm(args, rank, local_rank, world):
         },
         "checks": {"finite": finite, "abs_sum_r": checksum},
     }
+    if epilogue is not None:
+        line["polarimetry_epilogue"] = epilogue
     if gather is not None:
         line["gather"] = gather
     if world == 1 and not args.no_cpu_baseline:
