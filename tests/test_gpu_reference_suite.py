@@ -271,3 +271,61 @@ def test_mixed_jones_state_power(api):
     a_s, a_p = pair
     refl = abs(s.r_pp * a_p + s.r_sp * a_s) ** 2 + abs(s.r_ps * a_p + s.r_ss * a_s) ** 2
     assert float(summ["R"]) == pytest.approx(float(refl), abs=1e-9)
+
+
+# ---- tests/test_integration.py of the reference: workflows per material, multilayers, consistency ----
+
+def _simple_on(material, frequency, **exit_kw):
+    layer = {"type": "Semi Infinite Anisotropic Layer", "material": material, "rotationX": 0, "rotationY": 90, "rotationZ": 0}
+    layer.update(exit_kw)
+    return {"ScenarioData": {"type": "Simple", "incidentAngle": 45.0, "azimuthal_angle": 0.0, "frequency": frequency},
+            "Layers": [{"type": "Ambient Incident Layer", "permittivity": 50.0},
+                       {"type": "Isotropic Middle-Stack Layer", "thickness": 0.1}, layer]}
+
+
+@pytest.mark.parametrize("material,frequency", [("Quartz", 500.0), ("Sapphire", 500.0), ("GalliumOxide", 600.0)])
+def test_material_workflows(api, material, frequency):
+    s = run(api, _simple_on(material, frequency))
+    for name in ("r_pp", "r_ss", "r_ps", "r_sp"):
+        assert getattr(s, name) is not None and np.isfinite(getattr(s, name))
+    assert 0 <= abs(s.r_pp) ** 2 <= 1 + 1e-12 and 0 <= abs(s.r_ss) ** 2 <= 1 + 1e-12
+    m = api.Mueller(s)
+    m.set_incident_polarization("linear", angle=0)
+    m.add_optical_component("anisotropic_sample")
+    assert 0 <= float(m.get_reflectivity()) <= 1 + 1e-12
+
+
+def test_three_layer_structure_and_complex_gap(api):
+    calcite = {"material": "Calcite", "rotationX": 0, "rotationY": 90, "rotationZ": 0}
+    payload = {"ScenarioData": SIMPLE["ScenarioData"],
+               "Layers": [{"type": "Ambient Incident Layer", "permittivity": 50.0},
+                          {"type": "Isotropic Middle-Stack Layer", "thickness": 0.1, "permittivity": 1.0},
+                          dict(calcite, type="Crystal Layer", thickness=0.5),
+                          {"type": "Isotropic Middle-Stack Layer", "thickness": 0.1, "permittivity": 1.0},
+                          dict(calcite, type="Semi Infinite Anisotropic Layer")]}
+    s = run(api, payload)
+    assert len(s.layers) == 5 and np.isfinite(s.r_pp)
+    lossy_gap = {"ScenarioData": SIMPLE["ScenarioData"],
+                 "Layers": [{"type": "Ambient Incident Layer", "permittivity": 50.0},
+                            {"type": "Isotropic Middle-Stack Layer", "thickness": 0.1, "permittivity": {"real": 2.5, "imag": 0.1}},
+                            dict(calcite, type="Semi Infinite Anisotropic Layer")]}
+    s2 = run(api, lossy_gap)
+    assert np.isfinite(s2.r_pp) and abs(s2.r_pp) ** 2 <= 1 + 1e-12
+
+
+def test_reciprocity_and_rotation_by_pi(api):
+    """Un-rotated uniaxial exit: no polarisation conversion (r_ps = r_sp ~ 0, the reference's
+    'reciprocity' check); rotating the crystal by 180 degrees about z is the same crystal."""
+    s = run(api, SIMPLE)
+    assert abs(s.r_ps) <= 1e-6 and abs(s.r_sp) <= 1e-6
+    rotated = copy.deepcopy(SIMPLE)
+    rotated["Layers"][2]["rotationZ"] = 180
+    s2 = run(api, rotated)
+    assert abs(s2.r_pp - s.r_pp) <= 1e-9 and abs(s2.r_ss - s.r_ss) <= 1e-9
+
+
+@pytest.mark.parametrize("payload", [SIMPLE, INCIDENT, AZIMUTHAL], ids=["Simple", "Incident", "Azimuthal"])
+def test_total_reflectivity_bound_across_scenarios(api, payload):
+    s = run(api, payload)
+    total = np.abs(s.r_pp) ** 2 + np.abs(s.r_ss) ** 2 + np.abs(s.r_ps) ** 2 + np.abs(s.r_sp) ** 2
+    assert np.all(total <= 2.0 + 1e-9)
