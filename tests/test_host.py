@@ -221,3 +221,40 @@ def test_result_shape_follows_reference_broadcasting():
         assert squeezed == np.shape(ref["r_pp"]), f"seed {seed}: {plan.fabt_shape} vs {np.shape(ref['r_pp'])}"
         seen.add((entry["payload"]["ScenarioData"]["type"], len(squeezed)))
     assert len(seen) >= 5  # several scenario types and collapsed / full ranks were exercised
+
+
+def _plan_for(layers, sd=None):
+    sd = sd or {"type": "Incident"}
+    return planmod.build_plan(ScenarioSetup(sd, n_incident=8), layers)
+
+
+def test_fast_path_hint_and_scalar_detection():
+    """Planner hints the kernels rely on: `fast_path` (every crystal keeps z as a principal axis up to
+    the reference's hidden 1e-8 tilt), `eps_scalar` (isotropic crystal: closed-form modes) and the
+    stored Ry*Rx rotation (identity for a scalar table)."""
+    prism = {"type": "Ambient Incident Layer", "permittivity": 12.5}
+
+    def film(material, **rot):
+        return dict({"type": "Crystal Layer", "material": material, "thickness": 0.1}, **rot)
+
+    def exit_(material, **rot):
+        return dict({"type": "Semi Infinite Anisotropic Layer", "material": material}, **rot)
+
+    untilted = _plan_for([prism, film("hBN"), exit_("SiC")])
+    assert untilted.fast_path
+    assert untilted.layers[1].eps_scalar and not untilted.layers[0].eps_scalar
+    np.testing.assert_array_equal(untilted.layers[1].rotation_xy, np.eye(3))
+    # the hidden tilt is in the table: xz of the rotated hBN tensor is ~1e-8 (eps_xx - eps_zz), not 0
+    full = materials.unpack_symmetric(untilted.layers[0].eps)
+    assert 0 < np.abs(full[:, 0, 2]).max() < 1e-6 * np.abs(full[:, 0, 0]).max()
+    assert _plan_for([prism, film("hBN", rotationZ=37.0), exit_("Calcite", rotationY=90)]).fast_path
+    assert _plan_for([prism, film("MoO3", rotationY=180), exit_("Quartz", rotationY=90, rotationZ=12)]).fast_path
+    assert not _plan_for([prism, film("hBN", rotationY=30), exit_("SiC")]).fast_path
+    assert not _plan_for([prism, film("hBN"), exit_("Quartz", rotationX=45)]).fast_path
+    # an isotropic crystal may be tilted at will: R (eps I) R^T = eps I
+    assert _plan_for([prism, film("hBN"), exit_("SiC", rotationY=33, rotationX=12)]).fast_path
+    # no crystal at all: nothing to hint against
+    iso = _plan_for([prism, {"type": "Isotropic Middle-Stack Layer", "thickness": 0.2},
+                     {"type": "Semi Infinite Isotropic Layer", "permittivity": 2.0}],
+                    {"type": "Incident", "frequency": [900.0, 1000.0]})
+    assert iso.fast_path
