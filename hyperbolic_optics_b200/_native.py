@@ -11,10 +11,11 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 9
+HO_ABI_VERSION = 10
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
+HO_PROTOCOL_AUTO, HO_PROTOCOL_SINGLE, HO_PROTOCOL_FAST_FIXUP = 0, 1, 2
 
 
 class c128(C.Structure):
@@ -36,6 +37,8 @@ class Problem(C.Structure):
     _fields_ = [
         ("A", C.c_int32), ("B", C.c_int32), ("F", C.c_int32), ("T", C.c_int32),
         ("n_layers", C.c_int32), ("backend", C.c_int32), ("hint_fast_path", C.c_int32),
+        ("protocol", C.c_int32), ("tsweep_groups", C.c_int32), ("reserved0", C.c_int32),
+        ("work", C.c_void_p), ("work_capacity", C.c_int64),
         ("kx", C.c_void_p), ("k0", C.c_void_p),
         ("prism_inv_cos", C.c_void_p), ("prism_inv_ncos", C.c_void_p),
         ("prism_inv_n", C.c_double),

@@ -187,32 +187,9 @@ template <typename T> __device__ __forceinline__ void ferrari(cx<T> c3, cx<T> c2
 // kernel.  An FP32 Ferrari was tried (it would run on the FP32 pipe next to the FP64 work) and
 // rejected: when both root pairs are nearly double (near-normal incidence on a c-cut uniaxial
 // film) the resolvent discriminant cancels catastrophically in FP32 and the start roots come out
-// ~8 % off with the wrong sign of Im -> wrong forward/backward classification (found by
-// tests/test_gpu_parity.py::test_backends_agree_at_scale).  -DHO_FERRARI_FP32 re-enables it.
+// ~8 % off with the wrong sign of Im -> wrong forward/backward classification.
 __device__ __forceinline__ void start_roots(cx<double> c3, cx<double> c2, cx<double> c1, cx<double> c0, cx<double> lam[4]) {
-#ifndef HO_FERRARI_FP32
   ferrari(c3, c2, c1, c0, lam);
-#else
-  cx<float> f3 = mk<float>((float)c3.re, (float)c3.im), f2 = mk<float>((float)c2.re, (float)c2.im);
-  cx<float> f1 = mk<float>((float)c1.re, (float)c1.im), f0 = mk<float>((float)c0.re, (float)c0.im);
-  float sc = fmaxf(fmaxf(cabs(f3), sqrtf(cabs(f2))), fmaxf(cbrtf(cabs(f1)), sqrtf(sqrtf(cabs(f0)))));
-  if (!(sc > 0.f) || !(sc < 3.0e38f)) sc = 1.f;
-  float is = 1.f / sc, is2 = is * is;
-  cx<float> l32[4];
-  ferrari(is * f3, is2 * f2, (is2 * is) * f1, (is2 * is2) * f0, l32);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    cx<double> x = mk<double>((double)(sc * l32[i].re), (double)(sc * l32[i].im));
-    cx<double> pv = fma(fma(fma(x + c3, x, c2), x, c1), x, c0);
-    cx<double> dv = fma(fma(4.0 * x + 3.0 * c3, x, 2.0 * c2), x, c1);
-    double dn = norm2(dv);
-    if (dn > 0.0) {
-      cx<double> step = pv * mk<double>(dv.re / dn, -dv.im / dn);
-      if (norm2(step) <= 0.25 * norm2(x)) x = x - step;
-    }
-    lam[i] = x;
-  }
-#endif
 }
 __device__ __forceinline__ void start_roots(cx<float> c3, cx<float> c2, cx<float> c1, cx<float> c0, cx<float> lam[4]) {
   cx<double> l64[4];

@@ -507,6 +507,11 @@ int validate(const ho_problem_t* p, int64_t n_begin, int64_t n_end) {
   if (p->backend != HO_BACKEND_TRANSFER && p->backend != HO_BACKEND_SCATTERING)
     return fail(HO_ERR_BAD_ARGUMENT, "unknown backend");
   if (!p->kx || !p->k0 || !p->prism_inv_cos || !p->prism_inv_ncos) return fail(HO_ERR_BAD_ARGUMENT, "missing axis table");
+  if (p->protocol != HO_PROTOCOL_AUTO && p->protocol != HO_PROTOCOL_SINGLE && p->protocol != HO_PROTOCOL_FAST_FIXUP)
+    return fail(HO_ERR_BAD_ARGUMENT, "unknown launch protocol");
+  if (p->protocol == HO_PROTOCOL_FAST_FIXUP && (!p->work || p->work_capacity < 0))
+    return fail(HO_ERR_BAD_ARGUMENT, "HO_PROTOCOL_FAST_FIXUP needs a work list");
+  if (p->tsweep_groups < -1 || p->tsweep_groups > 32) return fail(HO_ERR_BAD_ARGUMENT, "tsweep_groups must be -1, 0 or 1..32");
   const int64_t N = (int64_t)p->A * p->B * p->F * p->T;
   if (n_begin < 0 || n_end < n_begin || n_end > N) return fail(HO_ERR_BAD_ARGUMENT, "point range outside the grid");
   for (int l = 0; l < p->n_layers; ++l) {
@@ -537,76 +542,82 @@ int validate(const ho_problem_t* p, int64_t n_begin, int64_t n_end) {
   return HO_OK;
 }
 
-// Work list of the fast-path protocol: one library-owned buffer per (device, stream), grown on
-// demand and kept (n/2 bytes: 50 MB for 1e8 points).  Work on one stream is ordered, so the
-// buffer can be reused by the next launch on that stream without synchronisation.
-unsigned char* work_scratch(size_t bytes, cudaStream_t stream) {
-  struct Slot { int dev; cudaStream_t stream; unsigned char* ptr; size_t cap; };
+// Every entry point runs on the device that owns the caller's buffers, whatever device is current
+// in the calling thread (a Structure(device="cuda:1") while cuda:0 is current must not launch on
+// GPU 0 over pointers of GPU 1): the device is read from the pointer, made current for the call
+// and restored afterwards.  The stream handle must belong to that device.
+struct DeviceScope {
+  int prev = -1, dev = -1;
+  bool switched = false, ok = true;
+  explicit DeviceScope(const void* device_ptr) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); ok = false; return; }
+    dev = prev;
+    cudaPointerAttributes attr;
+    if (device_ptr && cudaPointerGetAttributes(&attr, device_ptr) == cudaSuccess) {
+      if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) dev = attr.device;
+    } else {
+      cudaGetLastError();
+    }
+    if (dev != prev) { ok = cudaSetDevice(dev) == cudaSuccess; switched = ok; }
+  }
+  ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
+// SM count and resident CTAs per SM of a kernel, looked up once per (device, kernel, shape): the
+// occupancy query costs microseconds, which is visible when a launch is ~1 ms (strong scaling).
+struct Limits { int sms, per_sm; };
+Limits launch_limits(const void* kernel, int threads, size_t smem) {
+  struct Key { int dev; const void* kernel; int threads; size_t smem; Limits lim; };
   static std::mutex mu;
-  static std::vector<Slot> slots;
+  static std::vector<Key> cache;
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
-  for (Slot& s : slots) {
-    if (s.dev == dev && s.stream == stream) {
-      if (s.cap >= bytes) return s.ptr;
-      cudaStreamSynchronize(stream);  // the old buffer may still be in use by queued launches
-      cudaFree(s.ptr);
-      s.ptr = nullptr; s.cap = 0;
-      if (cudaMalloc((void**)&s.ptr, bytes + bytes / 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-      s.cap = bytes + bytes / 2;
-      return s.ptr;
-    }
-  }
-  Slot s{dev, stream, nullptr, 0};
-  if (cudaMalloc((void**)&s.ptr, bytes + bytes / 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  s.cap = bytes + bytes / 2;
-  slots.push_back(s);
-  return s.ptr;
+  for (const Key& k : cache)
+    if (k.dev == dev && k.kernel == kernel && k.threads == threads && k.smem == smem) return k.lim;
+  Limits lim{148, 1};
+  cudaDeviceGetAttribute(&lim.sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lim.per_sm, kernel, threads, smem) != cudaSuccess) cudaGetLastError();
+  if (lim.per_sm < 1) lim.per_sm = 1;
+  cache.push_back(Key{dev, kernel, threads, smem, lim});
+  return lim;
 }
 
 int grid_for(int64_t n, const void* kernel) {
-  int dev = 0, sms = 148, per_sm = 4;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-  if (per_sm < 1) per_sm = 1;
+  const Limits lim = launch_limits(kernel, kThreads, 0);
   // grid-stride over at most 32 waves of resident CTAs (measured on C1-C4 against 2, 8 and
   // "one point per thread": 32 is best or within 1 % for both recursions)
   int waves = 32;
-  if (const char* env = getenv("HO_B200_WAVES")) waves = atoi(env);  // tuning hook; 0 = one point per thread
+#ifdef HO_TUNING_HOOKS
+  if (const char* env = getenv("HO_B200_WAVES")) waves = atoi(env);  // 0 = one point per thread
+#endif
   int64_t want = (n + kThreads - 1) / kThreads;
   if (want < 1) want = 1;
   if (waves <= 0) return (int)(want < 0x7fffffff ? want : 0x7fffffff);
-  int64_t cap = (int64_t)sms * per_sm * waves;
+  int64_t cap = (int64_t)lim.sms * lim.per_sm * waves;
   return (int)(want < cap ? want : cap);
 }
 
 // Thickness-axis launch: groups per warp as large as possible (reuse) while still leaving
-// enough warps to fill the device.  HO_B200_TSWEEP=0 (test hook) forces one thread per point,
-// HO_B200_TSWEEP_GPW=n forces the groups per warp.
+// enough warps to fill the device; ho_problem_t.tsweep_groups overrides the choice.
 template <bool STABLE, bool NM, bool POWER>
 int launch_tsweep(const ho_problem_t* p, const OutPtrs<double>& out, int64_t n_begin, int64_t n_end, int swept,
                   cudaStream_t stream) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = launch_limits((const void*)tsweep_kernel<STABLE, NM, POWER>, kSweepThreads, 0).sms;
   const int64_t groups = (n_end - 1) / p->T - n_begin / p->T + 1;
   int gpw = 32;
   while (gpw > 1 && groups / gpw < (int64_t)sms * 16) gpw >>= 1;
-  if (const char* env = getenv("HO_B200_TSWEEP_GPW")) {
-    int v = atoi(env);
-    if (v >= 1 && v <= 32) gpw = v;
-  }
+  if (p->tsweep_groups >= 1 && p->tsweep_groups <= 32) gpw = p->tsweep_groups;
   int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) + (out.t_pp ? 8 : 0) : 0);
   row |= 1;  // odd row length: lane <-> row accesses in pass 0 are bank-conflict free
   const int wpb = kSweepThreads / 32;
   const size_t smem = (size_t)wpb * gpw * row * sizeof(double);
   auto kern = tsweep_kernel<STABLE, NM, POWER>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSweepThreads, smem);
-  if (per_sm < 1) per_sm = 1;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(HO_ERR_CUDA, "thickness-sweep kernel: %s", cudaGetErrorString(cudaGetLastError()));
+  const int per_sm = launch_limits((const void*)kern, kSweepThreads, smem).per_sm;
   const int64_t units = (groups + gpw - 1) / gpw;
   int64_t want = (units + wpb - 1) / wpb, cap = (int64_t)sms * per_sm * 4;
   const int grid = (int)(want < cap ? want : cap);
@@ -620,31 +631,26 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
     int swept = -1;
     for (int l = 0; l < p->n_layers; ++l)
       if (p->layers[l].n_thickness > 1) swept = l;
-    const char* env = getenv("HO_B200_TSWEEP");
-    if (p->T > 1 && swept >= 0 && !(env && atoi(env) == 0))
+    if (p->T > 1 && swept >= 0 && p->tsweep_groups >= 0)
       return launch_tsweep<STABLE, NM, POWER>(p, out, n_begin, n_end, swept, stream);
   }
   const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, false>;
   const int grid = grid_for(n_end - n_begin, kern);
   if constexpr (sizeof(T) == 8 && !POWER) {
-    const char* env = getenv("HO_B200_FAST_PATH");  // test hook: 0 disables, 1 forces the two-launch protocol
     // (below ~4M points the second launch costs more than the leaner kernel saves)
-    const bool want = env ? atoi(env) != 0 : (p->hint_fast_path != 0 && n_end - n_begin >= (int64_t)1 << 22);
-    if (want && out.r_pp && n_end - n_begin < ((int64_t)1 << 32)) {
+    const int64_t n = n_end - n_begin;
+    const bool want = p->protocol == HO_PROTOCOL_FAST_FIXUP ||
+                      (p->protocol == HO_PROTOCOL_AUTO && p->hint_fast_path != 0 && n >= (int64_t)1 << 22);
+    if (want && p->work && p->work_capacity >= 0 && out.r_pp && n < ((int64_t)1 << 32)) {
       const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, true>;
-      // room for 1/8 of the points on the list; beyond that the fix-up pass scans for the sentinel
-      int64_t cap = (n_end - n_begin) / 8 + 1024;
-      if (const char* c = getenv("HO_B200_FIXUP_CAP")) cap = atoll(c);  // test hook (0 forces the scan)
-      if (cap > (int64_t)0x7fffffff) cap = 0x7fffffff;
-      unsigned* work = (unsigned*)work_scratch((size_t)(cap + 1) * sizeof(unsigned), stream);
-      if (work) {
-        cudaMemsetAsync(work, 0, sizeof(unsigned), stream);
-        reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n_end - n_begin, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, work, (unsigned)cap);
-        if (env && atoi(env) == 2) return 0;  // test hook: leave the deferred points marked (r_pp = sentinel NaN)
-        reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, work, (unsigned)cap);
-        g_launches.fetch_add(1);
-        return 0;
-      }
+      // a list shorter than the deferred set makes the fix-up pass scan r_pp for the sentinel
+      const int64_t cap = p->work_capacity < (int64_t)0x7fffffff ? p->work_capacity : (int64_t)0x7fffffff;
+      if (cudaMemsetAsync(p->work, 0, sizeof(unsigned), stream) != cudaSuccess)
+        return fail(HO_ERR_CUDA, "work list reset failed: %s", cudaGetErrorString(cudaGetLastError()));
+      reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
+      reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, p->work, (unsigned)cap);
+      g_launches.fetch_add(1);
+      return 0;
     }
   }
   reflect_kernel<T, STABLE, NM, POWER, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr, 0u);
@@ -665,8 +671,9 @@ int launch(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_
   bool nm = true;
   for (int l = 0; l < p->n_layers; ++l)
     if ((p->layers[l].kind == HO_ANISO_FILM || p->layers[l].kind == HO_ANISO_EXIT) && !p->layers[l].mu_scalar) nm = false;
-  if (nm) launch_nm<T, STABLE, true>(p, out, n_begin, n_end, stream);
-  else launch_nm<T, STABLE, false>(p, out, n_begin, n_end, stream);
+  const int rc = nm ? launch_nm<T, STABLE, true>(p, out, n_begin, n_end, stream)
+                    : launch_nm<T, STABLE, false>(p, out, n_begin, n_end, stream);
+  if (rc) return rc;
   g_launches.fetch_add(1);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(HO_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
@@ -705,6 +712,8 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
   if (o.t_mode && !o.t_pp) return fail(HO_ERR_BAD_ARGUMENT, "t_mode needs the t_pp .. t_ss outputs");
   if (o.t_mode && o.t_mode_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "t_mode_stride is smaller than the point range");
   if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
+  DeviceScope scope(problem->kx);
+  if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<double, true>(problem, o, n_begin, n_end, s)
                                                    : launch<double, false>(problem, o, n_begin, n_end, s);
@@ -728,6 +737,8 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.t_mode = nullptr;
   o.t_mode_stride = 0;
   o.power_states = 2;
+  DeviceScope scope(problem->kx);
+  if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, n_begin, n_end, s)
                                                    : launch<float, false>(problem, o, n_begin, n_end, s);
@@ -763,15 +774,12 @@ int ho_polarimetry(const ho_polarimetry_t* q, int64_t n, void* cuda_stream) {
   if (!q || n < 0) return fail(HO_ERR_BAD_ARGUMENT, "ho_polarimetry: null request or negative n%s");
   if (n == 0) return HO_OK;
   if (!q->j_pp || !q->j_ps || !q->j_sp || !q->j_ss) return fail(HO_ERR_BAD_ARGUMENT, "ho_polarimetry: the four Jones planes are required%s");
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HO_ERR_NO_DEVICE, "ho_polarimetry: no CUDA device%s");
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  DeviceScope scope(q->j_pp);
+  if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "ho_polarimetry: cannot select the device that owns the Jones planes%s");
   const bool decomp = q->decomposition || q->decomposition_matrices;
   auto kern = decomp ? polarimetry_kernel<true> : polarimetry_kernel<false>;
-  int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPolarThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  int64_t want = (n + kPolarThreads - 1) / kPolarThreads, cap = (int64_t)sms * per_sm * 8;
+  const Limits lim = launch_limits((const void*)kern, kPolarThreads, 0);
+  int64_t want = (n + kPolarThreads - 1) / kPolarThreads, cap = (int64_t)lim.sms * lim.per_sm * 8;
   kern<<<(int)(want < cap ? want : cap), kPolarThreads, 0, (cudaStream_t)cuda_stream>>>(*q, n);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_polarimetry launch: %s", cudaGetErrorString(err));
@@ -785,6 +793,8 @@ int ho_material_table(const ho_material_t* m, const double* freq, int64_t F, ho_
   for (int a = 0; a < 3; ++a)
     if (m->n_osc[a] < 0 || m->n_osc[a] > HO_MAX_OSC) return fail(HO_ERR_BAD_ARGUMENT, "ho_material_table: more than HO_MAX_OSC oscillators%s");
   if (F == 0) return HO_OK;
+  DeviceScope scope(eps_out);
+  if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "ho_material_table: cannot select the device that owns the table%s");
   const int64_t want = (F + 127) / 128;
   material_table_kernel<<<(int)(want < 4096 ? want : 4096), 128, 0, (cudaStream_t)cuda_stream>>>(*m, freq, F, eps_out);
   cudaError_t err = cudaGetLastError();

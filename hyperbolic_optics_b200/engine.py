@@ -16,6 +16,11 @@ from . import _native as nat
 from . import plan as P
 
 BACKENDS = {"transfer": nat.HO_BACKEND_TRANSFER, "scattering": nat.HO_BACKEND_SCATTERING}
+# launch protocol of the point-per-thread kernels (include/ho_b200.h, ho_protocol): "auto" = the
+# fast-path kernel + fix-up launch for un-tilted plans of >= 2^22 points, "single" = the general
+# kernel alone, "fast" = always the two-launch protocol
+PROTOCOLS = {"auto": nat.HO_PROTOCOL_AUTO, "single": nat.HO_PROTOCOL_SINGLE, "fast": nat.HO_PROTOCOL_FAST_FIXUP}
+FAST_PATH_MIN_POINTS = 1 << 22
 
 
 def _require_cuda(device):
@@ -28,9 +33,16 @@ def _require_cuda(device):
 class DeviceProblem:
     """A ``StackPlan`` resident on one GPU plus the filled ``ho_problem_t`` descriptor."""
 
-    def __init__(self, plan: P.StackPlan, backend="transfer", device=None, device_tables=False):
+    def __init__(self, plan: P.StackPlan, backend="transfer", device=None, device_tables=False, protocol="auto",
+                 work_capacity=None, tsweep_groups=0, max_launch_points=None):
+        """``protocol`` / ``work_capacity`` / ``tsweep_groups``: launch details (``PROTOCOLS``; the
+        work list of the fast-path protocol holds ``work_capacity`` deferred points, default 1/8 of
+        the largest launch + 1024 -- ``max_launch_points`` bounds that launch, default the grid;
+        ``tsweep_groups``: 0 auto, -1 point per thread, 1..32 groups per warp on the thickness axis)."""
         if backend not in BACKENDS:
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
+        if protocol not in PROTOCOLS:
+            raise ValueError(f"Unknown protocol {protocol!r}; use one of {sorted(PROTOCOLS)}.")
         if len(plan.layers) > nat.HO_MAX_LAYERS:
             raise ValueError(f"at most {nat.HO_MAX_LAYERS} layers below the prism are supported")
         self.plan = plan
@@ -43,7 +55,19 @@ class DeviceProblem:
         d.n_layers = len(plan.layers)
         d.backend = BACKENDS[backend]
         d.hint_fast_path = 1 if plan.fast_path else 0
+        d.protocol = PROTOCOLS[protocol]
+        d.tsweep_groups = int(tsweep_groups)
         d.prism_inv_n = plan.prism_inv_n
+        # work list of the fast-path protocol: owned by this problem (freed with it), one in-flight
+        # launch sequence at a time (launches on one stream are ordered)
+        self.work = None
+        launch_points = min(plan.n_points, int(max_launch_points or plan.n_points))
+        wanted = protocol == "fast" or (protocol == "auto" and plan.fast_path and launch_points >= FAST_PATH_MIN_POINTS)
+        if wanted:
+            cap = int(work_capacity) if work_capacity is not None else launch_points // 8 + 1024
+            cap = max(0, min(cap, 0x7FFFFFFF))
+            self.work = torch.zeros(cap + 1, dtype=torch.int32, device=self.device)
+            d.work, d.work_capacity = self.work.data_ptr(), cap
         slots = [("kx", self._put_f64(plan.kx)), ("k0", self._put_f64(plan.k0)),
                  ("prism_inv_cos", self._put_f64(plan.prism_inv_cos)),
                  ("prism_inv_ncos", self._put_f64(plan.prism_inv_ncos))]
@@ -93,7 +117,7 @@ class DeviceProblem:
         plan = self.plan
         freq = np.atleast_1d(np.asarray(plan.frequency, dtype=np.float64))
         self._freq_dev = torch.from_numpy(np.ascontiguousarray(freq)).to(self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = torch.cuda.current_stream(self.device).cuda_stream   # the library selects the tables' device itself
         eps_slot = {i: slot for i, name, slot in layer_slots if name == "eps"}
         for i, lp in enumerate(plan.layers):
             mat = lp.material
@@ -153,6 +177,13 @@ class DeviceProblem:
     @property
     def n_points(self):
         return self.plan.n_points
+
+    def deferred_points(self):
+        """Number of points the fast-path kernel of the LAST launch left to the fix-up launch and
+        the capacity of the work list (synchronises; ``(None, 0)`` without a work list)."""
+        if self.work is None:
+            return None, 0
+        return int(self.work[0].item()) & 0xFFFFFFFF, int(self.desc.work_capacity)
 
 
 class DeviceOutputs:
@@ -219,11 +250,12 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
         nat.check(lib.ho_reflect_f32(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
 
 
-def measure_fp64_peak(iters=1 << 16):
-    """Achieved FP64 FMA FLOP/s of an 8-chain-per-thread FMA loop on the current device."""
-    _require_cuda(None)
+def measure_fp64_peak(iters=1 << 16, device=None):
+    """Achieved FP64 FMA FLOP/s of an 8-chain-per-thread FMA loop on ``device`` (default: current)."""
+    dev = _require_cuda(device)
     val = C.c_double(0.0)
-    nat.check(nat.lib().ho_measure_fp64_peak(int(iters), C.byref(val), torch.cuda.current_stream().cuda_stream))
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ho_measure_fp64_peak(int(iters), C.byref(val), torch.cuda.current_stream(dev).cuda_stream))
     return val.value
 
 

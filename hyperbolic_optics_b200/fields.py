@@ -115,12 +115,17 @@ class FieldProfile:
 
     def summary(self, polarization="p"):
         blk = self._block(polarization)
-        r, t = np.asarray(blk["R"]), np.asarray(blk["T"])
-        total = sum((np.asarray(a) for a in blk["A"]), start=np.zeros_like(r))
-        with np.errstate(invalid="ignore"):
-            residual = np.abs(r + t + total - 1.0)
+        r, t = blk["R"], blk["T"]
+        if isinstance(r, torch.Tensor):   # keep_on_device runs: the planes are CUDA tensors
+            total = sum(blk["A"], start=torch.zeros_like(r))
+            worst = float((r + t + total - 1.0).abs().max().item())
+        else:
+            r, t = np.asarray(r), np.asarray(t)
+            total = sum((np.asarray(a) for a in blk["A"]), start=np.zeros_like(r))
+            with np.errstate(invalid="ignore"):
+                worst = float(np.max(np.abs(r + t + total - 1.0)))
         return {"R": blk["R"], "T": blk["T"], "layers": self.layer_absorption(polarization),
-                "total_absorption": total, "conservation_residual": float(np.max(residual))}
+                "total_absorption": total, "conservation_residual": worst}
 
     def check_conservation(self, polarization="p"):
         return self.summary(polarization)["conservation_residual"]

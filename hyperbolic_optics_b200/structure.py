@@ -51,7 +51,7 @@ def _pinned(name, shape, dtype):
 class Structure:
     """Drop-in for ``hyperbolic_optics.structure.Structure`` on one B200."""
 
-    def __init__(self, device=None, chunk_points=1 << 22, device_tables=False):
+    def __init__(self, device=None, chunk_points=1 << 22, device_tables=False, protocol="auto", tsweep_groups=0):
         self.scenario = None
         self.layers = []
         self.incident_angle = None
@@ -67,11 +67,15 @@ class Structure:
         self.mueller = None
         self.stokes = None
         self.plan: StackPlan | None = None
+        self.problem = None   # engine.DeviceProblem of the last run
         self.device = device
         self.chunk_points = int(chunk_points)
         # True: eps(f) tables of the built-in dispersion models are evaluated on the GPU
         # (ho_material_table) instead of NumPy + H2D -- for sweeps with very many frequencies
         self.device_tables = bool(device_tables)
+        # launch details of the kernels (engine.PROTOCOLS / ho_problem_t.tsweep_groups); results do not depend on them
+        self.protocol = protocol
+        self.tsweep_groups = int(tsweep_groups)
         self.with_mueller = True
         self.with_power = False
         self.power_states = 2   # 4: additionally two mixed Jones states (execute(..., power="full"))
@@ -178,7 +182,10 @@ class Structure:
     def _run(self, backend):
         self._last_backend = backend
         plan = self.plan
-        prob = engine.DeviceProblem(plan, backend, self.device, device_tables=self.device_tables)
+        prob = engine.DeviceProblem(plan, backend, self.device, device_tables=self.device_tables, protocol=self.protocol,
+                                    tsweep_groups=self.tsweep_groups,
+                                    max_launch_points=None if self.keep_on_device else self.chunk_points)
+        self.problem = prob
         self.h2d_bytes = prob.h2d_bytes
         # R, T, A_i are backend-independent physics; they always come from the stable recursion,
         # which stays accurate where the transfer product is ill conditioned (two forward modes of a

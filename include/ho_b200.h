@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 9
+#define HO_ABI_VERSION 10
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -76,6 +76,14 @@ typedef struct {
   double exit_n;           /* HO_ISO_EXIT: sqrt(eps_exit) */
 } ho_layer_t;
 
+/* How ho_reflect launches the point-per-thread kernels (a launch detail: results are the same) */
+enum ho_protocol {
+  HO_PROTOCOL_AUTO = 0,      /* fast-path kernel + fix-up launch when hint_fast_path is set, a work list is
+                                supplied and the range has >= 2^22 points; the general kernel alone otherwise */
+  HO_PROTOCOL_SINGLE = 1,    /* the general kernel alone */
+  HO_PROTOCOL_FAST_FIXUP = 2 /* always the two-launch protocol (needs r_pp; any size, any stack) */
+};
+
 typedef struct {
   int32_t A, B, F, T;            /* canonical batch sizes (axes.py:21) */
   int32_t n_layers;              /* layers below the prism, <= HO_MAX_LAYERS */
@@ -84,6 +92,18 @@ typedef struct {
                                     tensors up to the reference's 1e-8 offsets), so the fast-path kernel applies
                                     to (almost) every point; a performance hint only -- points it cannot
                                     evaluate are finished by the general kernel either way */
+  int32_t protocol;              /* ho_protocol */
+  int32_t tsweep_groups;         /* thickness axis (T > 1): 0 = warp-cooperative kernel, groups per warp chosen by
+                                    the library; 1..32 = that many (f,a,b) groups per warp; -1 = one thread per
+                                    point, no reuse of the t-independent sub-stack */
+  int32_t reserved0;
+  /* Work list of the fast-path protocol: caller-owned device scratch of work_capacity + 1 uint32
+     (entry 0 = number of deferred points of the last launch, then their indices relative to
+     n_begin).  Launches that share a list must be ordered (same stream).  NULL: the general
+     kernel alone.  A list shorter than the deferred set is legal: the fix-up launch then finds the
+     points by a sentinel in r_pp instead. */
+  uint32_t* work;
+  int64_t work_capacity;
   const double* kx;              /* [A] sqrt(eps_prism) sin(theta)       structure.py:183 */
   const double* k0;              /* [F] 2 pi f                           structure.py:189 */
   const double* prism_inv_cos;   /* [A] 1/cos(theta)                     layers.py:109-152 */

@@ -15,8 +15,8 @@ product, the Redheffer star product).  Every function cites the reference
 "port" CPU baseline.
 
 Parity pin: validated against (a) the reference itself imported from
-``/root/reference`` on full grids (``tests/test_oracle_pin.py``, runs only where the
-reference is mounted) and (b) committed fixtures ``tests/golden/*.npz`` produced by
+``/root/reference`` on full grids (``tests/test_oracle.py``, the ``reference``-marked tests:
+they run only where the reference is mounted) and (b) committed fixtures ``tests/golden/*.npz`` produced by
 running the reference (``tests/golden/make_fixtures.py``) -- see DESIGN.md section 3.
 
 Batch convention (reference ``axes.py:21-22``): every array is canonical

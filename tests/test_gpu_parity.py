@@ -48,7 +48,7 @@ def test_fixture_parity(name, backend, built_library):
     prefix = "" if backend == "transfer" else "s_"
     err = parity.jones_error(got, fx, "", prefix)
     mask = parity.transfer_mask(fx) if backend == "transfer" else np.isfinite(err)
-    assert mask.mean() > 0.75
+    assert mask.mean() >= (parity.trusted_fraction(name) if backend == "transfer" else 1.0)   # scattering: unmasked
     worst = float(np.nanmax(err[mask]))
     # The 11-layer stack is specified for the scattering backend (BASELINE config 5).  Under the
     # *transfer* backend the reference's own result scatters by 2e-8 around the stable answer
@@ -264,7 +264,7 @@ def test_power_bookkeeping(name, backend, built_library):
 
 @pytest.mark.parametrize("name", ["c5_thickness_11layer", "thickness_axis_film"])
 @pytest.mark.parametrize("gpw", ["1", "4", "32"])
-def test_thickness_axis_reuse_matches_point_per_thread(name, gpw, built_library, monkeypatch):
+def test_thickness_axis_reuse_matches_point_per_thread(name, gpw, built_library):
     """The thickness-sweep kernel (the t-independent layers are swept once per (f, a, b) group by a
     warp and reused for every thickness sample, reference waves.py:317-326) gives the same results
     as one thread per point, for both backends, including sub-ranges that cut through a group."""
@@ -277,12 +277,9 @@ def test_thickness_axis_reuse_matches_point_per_thread(name, gpw, built_library,
     n = plan.n_points
     planes = 2 * (len(plan.layers) + 1)
     for backend in ("transfer", "scattering"):
-        prob = engine.DeviceProblem(plan, backend, "cuda:0")
-        monkeypatch.setenv("HO_B200_TSWEEP", "0")
+        prob = engine.DeviceProblem(plan, backend, "cuda:0", tsweep_groups=int(gpw))
         ref = engine.DeviceOutputs(n, prob.device, power_planes=planes)
-        engine.reflect(prob, ref)
-        monkeypatch.setenv("HO_B200_TSWEEP", "1")
-        monkeypatch.setenv("HO_B200_TSWEEP_GPW", gpw)
+        engine.reflect(engine.DeviceProblem(plan, backend, "cuda:0", tsweep_groups=-1), ref)   # one thread per point
         for lo, hi in ((0, n), (5, n - 3), (n // 2 + 1, n // 2 + 2)):
             got = engine.DeviceOutputs(hi - lo, prob.device, power_planes=planes)
             engine.reflect(prob, got, lo, hi)
@@ -365,7 +362,7 @@ def test_transmission_coefficients(name, backend, built_library):
     with np.errstate(all="ignore"):
         self_err = np.sqrt(sum(np.abs(fx[k] - fx["s_" + pair[k]]) ** 2 for k in T_KEYS) / den)
     mask = parity.transfer_mask(fx) & np.isfinite(err) & (self_err <= 1e-9)
-    assert mask.mean() > 0.75
+    assert mask.mean() >= parity.trusted_fraction(name, transmission=True)
     worst = float(np.nanmax(err[mask])) if np.ndim(err) else float(err)
     # eigenvector-based quantities: conditioned by the gap between the two forward eigenvalues
     # (Quartz at near-normal incidence), hence 1e-7 rather than the 1e-10 of r_*
@@ -456,8 +453,6 @@ def test_c5_full_size_properties(built_library):
     scattering backend, layer-resolved absorption): R from fluxes equals |r_co|^2 + |r_cross|^2,
     R + T + sum A_i = 1, every layer is passive, everything finite -- and the thickness-sweep
     kernel reproduces the point-per-thread kernel on the same grid."""
-    import os
-
     from hyperbolic_optics_b200 import engine
 
     plan = _config_bench_plan("c5")
@@ -467,13 +462,9 @@ def test_c5_full_size_properties(built_library):
     prob = engine.DeviceProblem(plan, "scattering", "cuda:0")
     out = engine.DeviceOutputs(n, prob.device, power_planes=planes)
     engine.reflect(prob, out)
-    os.environ["HO_B200_TSWEEP"] = "0"
-    try:
-        ref = engine.DeviceOutputs(n, prob.device, power_planes=planes)
-        engine.reflect(prob, ref)
-        torch.cuda.synchronize()
-    finally:
-        del os.environ["HO_B200_TSWEEP"]
+    ref = engine.DeviceOutputs(n, prob.device, power_planes=planes)
+    engine.reflect(engine.DeviceProblem(plan, "scattering", "cuda:0", tsweep_groups=-1), ref)   # one thread per point
+    torch.cuda.synchronize()
     assert bool(torch.isfinite(out.power).all()) and bool(torch.isfinite(torch.view_as_real(out.r)).all())
     assert float((out.power - ref.power).abs().max()) <= 1e-11
     assert float((out.r - ref.r).abs().max()) <= 1e-11
@@ -646,7 +637,7 @@ def test_transfer_backend_unmasked_vs_stable_reference(name, built_library):
 
 @pytest.mark.parametrize("name", ["c4_fullsweep_hbn_sic", "dispersion_calcite", "multilayer_incident", "c1_incident_calcite",
                                   "gallium_oxide_incident", "magnetic_gap_incident", "dispersion_iso_exit"])
-def test_fast_path_protocol_equals_general_kernel(name, built_library, monkeypatch):
+def test_fast_path_protocol_equals_general_kernel(name, built_library):
     """Fast-path kernel + fix-up launch (sentinel protocol) vs the general kernel alone: same
     results whether the fast path evaluates every point (un-tilted thin stacks), none (tilted
     crystal: every point bails at the biquadratic test) or a part (thick film: bails per point)."""
@@ -658,16 +649,12 @@ def test_fast_path_protocol_equals_general_kernel(name, built_library, monkeypat
     plan = build_plan(sc, payload["Layers"])
     n = plan.n_points
     for backend in ("transfer", "scattering"):
-        prob = engine.DeviceProblem(plan, backend, "cuda:0")
         res = {}
-        # "1": deferred points on the compacted work list; "scan": list overflowed (cap 0), the
+        # "1": deferred points on the compacted work list; "scan": list overflowed (capacity 0), the
         # fix-up pass finds them by the sentinel in r_pp
         for flag in ("0", "1", "scan"):
-            monkeypatch.setenv("HO_B200_FAST_PATH", "0" if flag == "0" else "1")
-            if flag == "scan":
-                monkeypatch.setenv("HO_B200_FIXUP_CAP", "0")
-            else:
-                monkeypatch.delenv("HO_B200_FIXUP_CAP", raising=False)
+            prob = engine.DeviceProblem(plan, backend, "cuda:0", protocol="single" if flag == "0" else "fast",
+                                        work_capacity=0 if flag == "scan" else None)
             out = engine.DeviceOutputs(n, prob.device)
             before = engine.launch_count()
             engine.reflect(prob, out)

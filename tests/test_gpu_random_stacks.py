@@ -82,11 +82,11 @@ def random_case(seed):
     return {"payload": {"ScenarioData": sd, "Layers": layers}, "grid": grid}
 
 
-def _gpu(entry, backend):
+def _gpu(entry, backend, protocol="auto"):
     from hyperbolic_optics_b200 import Structure
 
     inc, az = P.angle_overrides(entry)
-    s = Structure(device="cuda:0")
+    s = Structure(device="cuda:0", protocol=protocol)
     s.get_scenario(entry["payload"]["ScenarioData"])
     if inc is not None:
         s.scenario.incident_angle = inc
@@ -268,12 +268,10 @@ def untilted_case(seed):
 
 @pytest.mark.parametrize("forced", ["default", "fast-path protocol"])
 @pytest.mark.parametrize("block", range(3))
-def test_untilted_random_stacks_match_oracle(block, forced, built_library, monkeypatch):
+def test_untilted_random_stacks_match_oracle(block, forced, built_library):
     from hyperbolic_optics_b200 import engine
     from oracle import reference_port as oracle
 
-    if forced != "default":
-        monkeypatch.setenv("HO_B200_FAST_PATH", "1")
     worst, hinted, two_launch = 0.0, 0, 0
     for seed in range(3000 + 25 * block, 3000 + 25 * (block + 1)):
         entry = untilted_case(seed)
@@ -284,7 +282,7 @@ def test_untilted_random_stacks_match_oracle(block, forced, built_library, monke
             continue
         for backend in ("scattering", "transfer"):
             before = engine.launch_count()
-            s = _gpu(entry, backend)
+            s = _gpu(entry, backend, protocol="auto" if forced == "default" else "fast")
             launches = engine.launch_count() - before
             hinted += bool(s.plan.fast_path)
             two_launch += launches >= 3          # fast + fix-up (+ the power launch of _gpu)

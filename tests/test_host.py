@@ -162,7 +162,9 @@ def test_struct_layout_matches_header(tmp_path):
         'offsetof(ho_problem_t, layers), offsetof(ho_layer_t, eps), offsetof(ho_layer_t, exit_n), '
         'sizeof(ho_outputs_t), offsetof(ho_outputs_t, t_mode), sizeof(ho_polarimetry_t), '
         'offsetof(ho_polarimetry_t, j_post), offsetof(ho_polarimetry_t, mueller)); '
-        'printf("%zu %zu %zu\\n", sizeof(ho_material_t), offsetof(ho_material_t, amp), offsetof(ho_material_t, rot)); return 0; }\n')
+        'printf("%zu %zu %zu\\n", sizeof(ho_material_t), offsetof(ho_material_t, amp), offsetof(ho_material_t, rot)); '
+        'printf("%zu %zu %zu\\n", offsetof(ho_problem_t, work), offsetof(ho_problem_t, work_capacity), offsetof(ho_problem_t, kx)); '
+        'return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
@@ -170,7 +172,7 @@ def test_struct_layout_matches_header(tmp_path):
                    nat.LayerDesc.eps.offset, nat.LayerDesc.exit_n.offset, ctypes.sizeof(nat.Outputs),
                    nat.Outputs.t_mode.offset, ctypes.sizeof(nat.Polarimetry), nat.Polarimetry.j_post.offset,
                    nat.Polarimetry.mueller.offset, ctypes.sizeof(nat.MaterialDesc), nat.MaterialDesc.amp.offset,
-                   nat.MaterialDesc.rot.offset]
+                   nat.MaterialDesc.rot.offset, nat.Problem.work.offset, nat.Problem.work_capacity.offset, nat.Problem.kx.offset]
 
 
 def test_product_never_imports_oracle():
