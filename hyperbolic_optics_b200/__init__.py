@@ -5,6 +5,7 @@ Drop-in for the hot path of hyperbolic-optics 0.3.0 (``Structure.execute`` ->
 hand-written sm_100a CUDA kernels through the C ABI in ``include/ho_b200.h``.
 """
 
+from .dropin import install, installed, uninstall
 from .fields import FieldProfile
 from .materials import create_material, list_materials
 from .mueller import Mueller
@@ -14,4 +15,5 @@ from .structure import Structure
 from .sweep import ThicknessSweep
 
 __version__ = "0.1.0"
-__all__ = ["Structure", "ScenarioSetup", "Mueller", "Jones", "compose_jones", "FieldProfile", "ThicknessSweep", "create_material", "list_materials", "__version__"]
+__all__ = ["Structure", "ScenarioSetup", "Mueller", "Jones", "compose_jones", "FieldProfile", "ThicknessSweep", "create_material", "list_materials",
+           "install", "uninstall", "installed", "__version__"]

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 10
+HO_ABI_VERSION = 11
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -79,6 +79,14 @@ class Polarimetry(C.Structure):
     ]
 
 
+class LayerModes(C.Structure):
+    _fields_ = [
+        ("matrix", C.c_void_p), ("modes", C.c_void_p), ("kz", C.c_void_p), ("fields", C.c_void_p), ("poynting", C.c_void_p),
+        ("mA", C.c_int32), ("mB", C.c_int32), ("mF", C.c_int32), ("mT", C.c_int32),
+        ("pA", C.c_int32), ("pB", C.c_int32), ("pF", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 HO_MAX_OSC = 8
 HO_MAT_TOLO, HO_MAT_MONOCLINIC = 1, 2
 
@@ -94,8 +102,8 @@ class MaterialDesc(C.Structure):
     ]
 
 
-EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_material_table", "ho_measure_fp64_peak", "ho_launch_count",
-           "ho_abi_version", "ho_last_error")
+EXPORTS = ("ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_material_table", "ho_layer_modes", "ho_transfer_matrix",
+           "ho_measure_fp64_peak", "ho_launch_count", "ho_abi_version", "ho_last_error")
 
 
 def library_path() -> Path:
@@ -118,6 +126,10 @@ def load():
     lib.ho_polarimetry.restype = C.c_int
     lib.ho_material_table.argtypes = [C.POINTER(MaterialDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.ho_material_table.restype = C.c_int
+    lib.ho_layer_modes.argtypes = [C.POINTER(Problem), C.c_int32, C.POINTER(LayerModes), C.c_void_p]
+    lib.ho_layer_modes.restype = C.c_int
+    lib.ho_transfer_matrix.argtypes = [C.POINTER(Problem), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.ho_transfer_matrix.restype = C.c_int
     lib.ho_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
     lib.ho_measure_fp64_peak.restype = C.c_int
     lib.ho_launch_count.argtypes = []

@@ -487,6 +487,12 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
   }
 }
 
+}  // namespace
+
+#include "ho_modes.cuh"
+
+namespace {
+
 __global__ void fp64_peak_kernel(int iters, double* sink) {
   double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3;
   double a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
@@ -799,6 +805,72 @@ int ho_material_table(const ho_material_t* m, const double* freq, int64_t F, ho_
   material_table_kernel<<<(int)(want < 4096 ? want : 4096), 128, 0, (cudaStream_t)cuda_stream>>>(*m, freq, F, eps_out);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_material_table launch: %s", cudaGetErrorString(err));
+  g_launches.fetch_add(1);
+  return HO_OK;
+}
+
+int ho_layer_modes(const ho_problem_t* problem, int32_t layer, const ho_layer_modes_t* out, void* cuda_stream) {
+  int rc = validate(problem, 0, 0);
+  if (rc) return rc;
+  if (!out) return fail(HO_ERR_BAD_ARGUMENT, "ho_layer_modes: outputs is NULL");
+  if (layer < 0 || layer >= problem->n_layers) return fail(HO_ERR_BAD_ARGUMENT, "ho_layer_modes: layer index out of range");
+  const ho_layer_t& L = problem->layers[layer];
+  if (L.kind == HO_ISO_EXIT) return fail(HO_ERR_BAD_ARGUMENT, "ho_layer_modes: the isotropic exit has no wave profile (layers.py:637-666)");
+  auto axis_ok = [](int m, int full) { return m == 1 || m == full; };
+  if (!axis_ok(out->mA, problem->A) || !axis_ok(out->mB, problem->B) || !axis_ok(out->mF, problem->F) || !axis_ok(out->mT, problem->T))
+    return fail(HO_ERR_BAD_ARGUMENT, "ho_layer_modes: matrix batch sizes must be 1 or the problem's");
+  if (out->pA != out->mA || out->pB != out->mB || (out->pF != 1 && out->pF != out->mF))
+    return fail(HO_ERR_BAD_ARGUMENT, "ho_layer_modes: profile batch sizes must follow the matrix's");
+  if (out->mT > 1 && L.n_thickness <= 1) return fail(HO_ERR_BAD_ARGUMENT, "ho_layer_modes: mT > 1 on a layer whose thickness is not swept");
+  const void* any = out->matrix ? (const void*)out->matrix : out->modes ? (const void*)out->modes : out->kz ? (const void*)out->kz
+                    : out->fields ? (const void*)out->fields : (const void*)out->poynting;
+  if (!any) return HO_OK;
+  DeviceScope scope(any);
+  if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "ho_layer_modes: cannot select the device that owns the outputs");
+  ModesOut o;
+  o.matrix = reinterpret_cast<ho::cx<double>*>(out->matrix);
+  o.modes = reinterpret_cast<ho::cx<double>*>(out->modes);
+  o.kz = reinterpret_cast<ho::cx<double>*>(out->kz);
+  o.fields = reinterpret_cast<ho::cx<double>*>(out->fields);
+  o.poynting = out->poynting;
+  o.mA = out->mA; o.mB = out->mB; o.mF = out->mF; o.mT = out->mT;
+  o.pA = out->pA; o.pB = out->pB; o.pF = out->pF;
+  const int64_t n = (int64_t)o.mA * o.mB * o.mF * o.mT;
+  const bool nm = L.kind == HO_ISO_FILM || L.mu_scalar;
+  const void* kern = nm ? (const void*)modes_kernel<true> : (const void*)modes_kernel<false>;
+  const Limits lim = launch_limits(kern, 128, 0);
+  int64_t want = (n + 127) / 128, cap = (int64_t)lim.sms * lim.per_sm * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (nm) modes_kernel<true><<<grid, 128, 0, s>>>(*problem, layer, o, n);
+  else modes_kernel<false><<<grid, 128, 0, s>>>(*problem, layer, o, n);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_layer_modes launch: %s", cudaGetErrorString(err));
+  g_launches.fetch_add(1);
+  return HO_OK;
+}
+
+int ho_transfer_matrix(const ho_problem_t* problem, ho_c128* gamma, int64_t n_begin, int64_t n_end, void* cuda_stream) {
+  int rc = validate(problem, n_begin, n_end);
+  if (rc) return rc;
+  if (!gamma) return fail(HO_ERR_BAD_ARGUMENT, "ho_transfer_matrix: gamma is NULL");
+  if (n_end == n_begin) return HO_OK;
+  DeviceScope scope(gamma);
+  if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "ho_transfer_matrix: cannot select the device that owns gamma");
+  bool nm = true;
+  for (int l = 0; l < problem->n_layers; ++l)
+    if ((problem->layers[l].kind == HO_ANISO_FILM || problem->layers[l].kind == HO_ANISO_EXIT) && !problem->layers[l].mu_scalar) nm = false;
+  const void* kern = nm ? (const void*)gamma_kernel<true> : (const void*)gamma_kernel<false>;
+  const Limits lim = launch_limits(kern, 128, 0);
+  const int64_t n = n_end - n_begin;
+  int64_t want = (n + 127) / 128, cap = (int64_t)lim.sms * lim.per_sm * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  ho::cx<double>* g = reinterpret_cast<ho::cx<double>*>(gamma);
+  if (nm) gamma_kernel<true><<<grid, 128, 0, s>>>(*problem, g, n_begin, n_end);
+  else gamma_kernel<false><<<grid, 128, 0, s>>>(*problem, g, n_begin, n_end);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(HO_ERR_CUDA, "ho_transfer_matrix launch: %s", cudaGetErrorString(err));
   g_launches.fetch_add(1);
   return HO_OK;
 }

@@ -261,3 +261,58 @@ def measure_fp64_peak(iters=1 << 16, device=None):
 
 def launch_count():
     return int(nat.lib().ho_launch_count())
+
+
+# ---- opt-in materialised objects --------------------------------
+def layer_batch_shape(plan: P.StackPlan, index):
+    """Canonical batch shapes ``(mA, mB, mF, mT), (pA, pB, pF)`` of layer ``index`` (below the prism)
+    as the reference's broadcast leaves them: the matrix of a film depends on F through ``k0``
+    (``waves.py:317-326``), its profile only through a dispersive tensor; an isotropic film does not
+    depend on the azimuth; the thickness axis only exists on the swept layer."""
+    lp = plan.layers[index]
+    finite = lp.kind in (P.KIND_ISO_FILM, P.KIND_ANISO_FILM)
+    crystal = lp.kind in (P.KIND_ANISO_FILM, P.KIND_ANISO_EXIT)
+    dispersive = crystal and (lp.eps.shape[0] > 1 or lp.mu.shape[0] > 1)
+    m_b = plan.B if crystal else 1
+    p_f = plan.F if dispersive else 1
+    m_f = plan.F if (finite or dispersive) else 1
+    m_t = plan.T if (lp.thickness is not None and lp.thickness.size > 1) else 1
+    return (plan.A, m_b, m_f, m_t), (plan.A, m_b, p_f)
+
+
+def layer_modes(problem: DeviceProblem, index, stream=None, matrix=True, profile=True):
+    """``ho_layer_modes`` for one Wave-built layer: dict of device tensors ``matrix``
+    ``[mA, mB, mF, mT, 4, 4]``, ``modes`` ``[pA, pB, pF, 1, 4, 4]``, ``kz`` ``[.., 4]``, ``fields``
+    ``[.., 6, 4]``, ``poynting`` ``[.., 3, 4]`` (canonical layout, reference ``axes.py:21-22``)."""
+    (m_a, m_b, m_f, m_t), (p_a, p_b, p_f) = layer_batch_shape(problem.plan, index)
+    dev = problem.device
+    out = {}
+    if matrix:
+        out["matrix"] = torch.empty((m_a, m_b, m_f, m_t, 4, 4), dtype=torch.complex128, device=dev)
+    if profile:
+        out["modes"] = torch.empty((p_a, p_b, p_f, 1, 4, 4), dtype=torch.complex128, device=dev)
+        out["kz"] = torch.empty((p_a, p_b, p_f, 1, 4), dtype=torch.complex128, device=dev)
+        out["fields"] = torch.empty((p_a, p_b, p_f, 1, 6, 4), dtype=torch.complex128, device=dev)
+        out["poynting"] = torch.empty((p_a, p_b, p_f, 1, 3, 4), dtype=torch.float64, device=dev)
+    q = nat.LayerModes()
+    for name in ("matrix", "modes", "kz", "fields", "poynting"):
+        if name in out:
+            setattr(q, name, out[name].data_ptr())
+    q.mA, q.mB, q.mF, q.mT, q.pA, q.pB, q.pF = m_a, m_b, m_f, m_t, p_a, p_b, p_f
+    handle = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    nat.check(nat.lib().ho_layer_modes(C.byref(problem.desc), int(index), C.byref(q), handle))
+    return out
+
+
+def transfer_matrix(problem: DeviceProblem, n_begin=0, n_end=None, out=None, stream=None):
+    """``ho_transfer_matrix``: Gamma of canonical points ``[n_begin, n_end)`` as a device tensor
+    ``[n, 4, 4]`` complex128 (reference ``structure.py:259-270``)."""
+    n_end = problem.n_points if n_end is None else n_end
+    n = n_end - n_begin
+    if out is None:
+        out = torch.empty((n, 4, 4), dtype=torch.complex128, device=problem.device)
+    elif out.shape[0] < n:
+        raise ValueError("gamma buffer is smaller than the requested point range")
+    handle = (stream or torch.cuda.current_stream(problem.device)).cuda_stream
+    nat.check(nat.lib().ho_transfer_matrix(C.byref(problem.desc), out.data_ptr(), n_begin, n_end, handle))
+    return out

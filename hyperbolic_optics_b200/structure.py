@@ -19,9 +19,13 @@ computes -- and returns -- only its contiguous slab of the slowest swept axis, `
 absorption for p and s incidence from the same launch, both backends; consumed by
 ``hyperbolic_optics_b200.FieldProfile``), ``device=`` / ``keep_on_device=``.
 
-What is *not* materialised: per-layer 4x4 matrices, eigenvector profiles and
-``transfer_matrix`` -- the kernel keeps a 4x2 plane in registers instead,
-so ``transfer_matrix`` stays ``None`` and ``layers[i].matrix`` does not exist.
+Per-layer 4x4 matrices, eigenvector profiles and ``transfer_matrix`` are not part of the
+reflection launch -- the kernel keeps a 4x2 plane in registers instead.
+They are *lazy*: reading ``structure.transfer_matrix``, ``layers[i].matrix`` or
+``layers[i].profile`` (what the reference's ``FieldProfile`` and ``scattering_coefficients`` do,
+``fields.py:87-97``, ``scattering.py:45-63``) launches the materialising kernels
+(``ho_transfer_matrix`` / ``ho_layer_modes``, 256 B per point) on the kept plan and caches the
+canonical ``[A, B, F, T, 4, 4]`` arrays.
 """
 
 from __future__ import annotations
@@ -32,6 +36,7 @@ import torch
 from . import engine, sharding
 from .plan import StackPlan, build_plan
 from .scenario import ScenarioSetup, present
+from .waves import LayerRecord, WaveProfile, iso_exit_matrix, prism_matrix
 
 _PINNED_POOL = {}
 
@@ -63,7 +68,7 @@ class Structure:
         self.r_pp = self.r_ss = self.r_ps = self.r_sp = None
         self.t_pp = self.t_ss = self.t_ps = self.t_sp = None
         self.mode_transmittance = None
-        self.transfer_matrix = None
+        self._gamma = None
         self.mueller = None
         self.stokes = None
         self.plan: StackPlan | None = None
@@ -107,7 +112,8 @@ class Structure:
     def get_layers(self, layer_data_list):
         """Host planning: resolves frequency, kx/k0 and per-layer tables (no device work)."""
         self.plan = build_plan(self.scenario, layer_data_list)
-        self.layers = [_PrismRecord(self.plan)] + list(self.plan.layers)
+        self.layers = [LayerRecord(self, 0)] + [LayerRecord(self, i + 1, lp) for i, lp in enumerate(self.plan.layers)]
+        self._gamma = None
         self.eps_prism = self.plan.eps_prism
         self.frequency = self.plan.frequency
         self.k_x = self.plan.kx.reshape(-1, 1, 1, 1)
@@ -122,6 +128,55 @@ class Structure:
     def calculate(self):
         """Transfer backend selected; the product itself is fused into the kernel launch."""
         self._backend = "transfer"
+
+    # -- lazy materialised objects (SURVEY 8 a10, a12, f-2) ------------------------------------
+    @property
+    def transfer_matrix(self):
+        """Gamma = M_prism M_1 ... M_exit, canonical ``[A, B, F, T, 4, 4]`` (reference
+        ``structure.py:259-270``); ``None`` until a transfer-backend run exists, like the reference
+        (its scattering backend never builds the product, ``structure.py:405-410``).  Computed on
+        first access by ``ho_transfer_matrix`` in launches of ``chunk_points`` points."""
+        if self._gamma is None and self.problem is not None and self._last_backend == "transfer":
+            if self.shard is not None:
+                raise ValueError("transfer_matrix is not available for a sharded run (the canonical order "
+                                 "is not the sharded one); execute the slab's payload unsharded instead")
+            plan, prob = self.plan, self.problem.with_backend("transfer")
+            shape = (plan.A, plan.B, plan.F, plan.T, 4, 4)
+            if self.keep_on_device:
+                self._gamma = engine.transfer_matrix(prob).reshape(shape)
+            else:
+                host = np.empty((plan.n_points, 4, 4), dtype=np.complex128)
+                chunk = min(plan.n_points, self.chunk_points)
+                buf = torch.empty((chunk, 4, 4), dtype=torch.complex128, device=prob.device)
+                for lo in range(0, plan.n_points, chunk):
+                    hi = min(plan.n_points, lo + chunk)
+                    engine.transfer_matrix(prob, lo, hi, out=buf)
+                    host[lo:hi] = buf[:hi - lo].cpu().numpy()
+                self._gamma = host.reshape(shape)
+        return self._gamma
+
+    @transfer_matrix.setter
+    def transfer_matrix(self, value):
+        self._gamma = value
+
+    def _materialise_layer(self, record):
+        """Fill ``record._matrix`` / ``record._profile`` (``layers[i].matrix``, ``.profile``)."""
+        if self.plan is None:
+            raise ValueError("Structure has no layers yet; call structure.execute(payload).")
+        if record.plan is None:
+            record._matrix = prism_matrix(self.plan)
+            return
+        if record.plan.kind == 4:   # isotropic exit: closed-form matrix, no Wave (layers.py:637-666)
+            record._matrix = iso_exit_matrix(record.plan)
+            return
+        if self.problem is None:
+            self.problem = engine.DeviceProblem(self.plan, self._backend, self.device, device_tables=self.device_tables,
+                                                protocol="single")
+        out = engine.layer_modes(self.problem, record._index - 1)
+        if not self.keep_on_device:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        record._matrix = out["matrix"]
+        record._profile = WaveProfile(out["fields"], out["kz"], out["poynting"])
 
     def calculate_reflectivity(self):
         self._run(self._backend)
@@ -300,13 +355,3 @@ class Structure:
 def _present_torch(t):
     lead = tuple(n for n in t.shape[:4] if n != 1)
     return t.reshape(lead + tuple(t.shape[4:]))
-
-
-class _PrismRecord:
-    """Layer-list entry for the incident medium (reference ``layers.py:432-460``)."""
-
-    type = "Ambient Incident Layer"
-    thickness = None
-
-    def __init__(self, plan):
-        self.eps_prism = plan.eps_prism

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 10
+#define HO_ABI_VERSION 11
 #define HO_MAX_LAYERS 24
 
 typedef struct { double re, im; } ho_c128;
@@ -226,6 +226,46 @@ typedef struct {
 /* freq: device [F] float64 (cm^-1); eps_out: device [F][6] complex128 (xx, xy, xz, yy, yz, zz) */
 int ho_material_table(const ho_material_t* material, const double* freq, int64_t F, ho_c128* eps_out,
                       void* cuda_stream);
+
+/* Opt-in materialised objects.  The reflection kernels never form
+   eigenvectors or 4x4 matrices; the reference, however, exposes them per layer and its own
+   consumers read them: FieldProfile (fields.py:78-97, 156-169, 358-390, 470-479) and
+   scattering_coefficients (scattering.py:45-63).  These two entry points write exactly those
+   arrays in the reference's CANONICAL [A, B, F, T, ...] layout (axes.py:21-22), HBM-bound at
+   256 B per point and layer.
+
+   ho_layer_modes: one Wave-built layer (HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT) ->
+     matrix   layer.matrix: exp(-i Delta k0 d) of a film (waves.py:298-335), [t0, 0, t1, 0] of a
+              semi-infinite crystal (waves.py:512-536); batch shape [mA][mB][mF][mT], an axis the
+              layer does not depend on has size 1 like in the reference's broadcast
+     modes    WaveProfile.tangential_modes()[0] (waves.py:72-96): rows Ex, Ey, Hx, Hy, columns
+              t0, t1, r0, r1 = numpy.linalg.eig's unit-norm eigenvectors (largest component real
+              positive, waves.py:270), split and ordered by wave_sorting (waves.py:256-296) and
+              sort_poynting_indices (waves.py:474-510); batch shape [pA][pB][pF]
+     kz       the same columns' eigenvalues
+     fields   WaveProfile.full_modes()[0]: rows Ex, Ey, Ez, Hx, Hy, Hz (waves.py:382-408)
+     poynting time-averaged Poynting vector, rows Px, Py, Pz (waves.py:410-420)
+   Any output pointer may be NULL.  In a degenerate eigenspace (isotropic medium: two equal kz) the
+   reference's basis is whatever LAPACK returns; here it is the (p, s) pair of SURVEY A.13. */
+typedef struct {
+  ho_c128* matrix;   /* [mA][mB][mF][mT][4][4] row-major */
+  ho_c128* modes;    /* [pA][pB][pF][4][4] */
+  ho_c128* kz;       /* [pA][pB][pF][4] */
+  ho_c128* fields;   /* [pA][pB][pF][6][4] */
+  double* poynting;  /* [pA][pB][pF][3][4] */
+  int32_t mA, mB, mF, mT; /* each 1 or the problem's A, B, F, T */
+  int32_t pA, pB, pF;     /* pA = mA, pB = mB, pF = 1 or mF */
+  int32_t reserved;
+} ho_layer_modes_t;
+int ho_layer_modes(const ho_problem_t* problem, int32_t layer, const ho_layer_modes_t* out, void* cuda_stream);
+
+/* structure.transfer_matrix (structure.py:259-270): Gamma = M_prism M_1 ... M_exit for canonical
+   points [n_begin, n_end), n = ((a*B + b)*F + f)*T + t; gamma: device [n_end - n_begin][4][4]
+   complex128 row-major.  Transfer-matrix semantics (overflows like the reference).  The exit
+   columns are in the reference's mode basis (see ho_layer_modes), so FieldProfile and
+   calculate_transmissivity run on it unchanged. */
+int ho_transfer_matrix(const ho_problem_t* problem, ho_c128* gamma, int64_t n_begin, int64_t n_end,
+                       void* cuda_stream);
 
 /* FP64 FMA-chain microbenchmark used as the roofline denominator: runs `iters` dependent
    FMA rounds on every SM and returns achieved FLOP/s (2 flops per FMA) in *flops_per_s. */

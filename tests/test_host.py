@@ -119,8 +119,8 @@ def test_present_squeezes_like_reference():
 def test_library_exports_every_declared_symbol(built_library):
     header = (ROOT / "include" / "ho_b200.h").read_text()
     declared = set(re.findall(r"\b(ho_[a-z0-9_]+)\s*\(", header))
-    assert {"ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_material_table", "ho_measure_fp64_peak", "ho_launch_count",
-            "ho_abi_version", "ho_last_error"} <= declared
+    assert {"ho_reflect", "ho_reflect_f32", "ho_polarimetry", "ho_material_table", "ho_layer_modes", "ho_transfer_matrix",
+            "ho_measure_fp64_peak", "ho_launch_count", "ho_abi_version", "ho_last_error"} <= declared
     for sym in declared:
         assert hasattr(built_library, sym), f"{sym} declared in ho_b200.h but not exported"
     from hyperbolic_optics_b200 import _native
@@ -147,6 +147,9 @@ def test_descriptor_validation_without_gpu(built_library):
     assert built_library.ho_polarimetry(ctypes.byref(req), 0, None) == 0  # empty range: nothing to do
     mat = nat.MaterialDesc()
     assert built_library.ho_material_table(ctypes.byref(mat), None, 4, None, None) == -1
+    modes = nat.LayerModes()
+    assert built_library.ho_layer_modes(ctypes.byref(prob), 0, ctypes.byref(modes), None) == -1
+    assert built_library.ho_transfer_matrix(ctypes.byref(prob), None, 0, 0, None) == -1
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -164,6 +167,7 @@ def test_struct_layout_matches_header(tmp_path):
         'offsetof(ho_polarimetry_t, j_post), offsetof(ho_polarimetry_t, mueller)); '
         'printf("%zu %zu %zu\\n", sizeof(ho_material_t), offsetof(ho_material_t, amp), offsetof(ho_material_t, rot)); '
         'printf("%zu %zu %zu\\n", offsetof(ho_problem_t, work), offsetof(ho_problem_t, work_capacity), offsetof(ho_problem_t, kx)); '
+        'printf("%zu %zu %zu\\n", sizeof(ho_layer_modes_t), offsetof(ho_layer_modes_t, mA), offsetof(ho_layer_modes_t, pF)); '
         'return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
@@ -172,7 +176,8 @@ def test_struct_layout_matches_header(tmp_path):
                    nat.LayerDesc.eps.offset, nat.LayerDesc.exit_n.offset, ctypes.sizeof(nat.Outputs),
                    nat.Outputs.t_mode.offset, ctypes.sizeof(nat.Polarimetry), nat.Polarimetry.j_post.offset,
                    nat.Polarimetry.mueller.offset, ctypes.sizeof(nat.MaterialDesc), nat.MaterialDesc.amp.offset,
-                   nat.MaterialDesc.rot.offset, nat.Problem.work.offset, nat.Problem.work_capacity.offset, nat.Problem.kx.offset]
+                   nat.MaterialDesc.rot.offset, nat.Problem.work.offset, nat.Problem.work_capacity.offset, nat.Problem.kx.offset,
+                   ctypes.sizeof(nat.LayerModes), nat.LayerModes.mA.offset, nat.LayerModes.pF.offset]
 
 
 def test_product_never_imports_oracle():
