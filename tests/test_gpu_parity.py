@@ -182,27 +182,34 @@ def test_device_resident_outputs_and_ranges(built_library):
     assert engine.launch_count() >= 2
 
 
-@pytest.mark.parametrize("name", ["c2_dispersion_moo3", "c1_incident_calcite", "c4_fullsweep_hbn_sic"])
-def test_complex64_path(name, built_library):
-    """Opt-in complex64 arithmetic: <= 1e-4 (north_star) against the complex128 kernel."""
-    from hyperbolic_optics_b200 import engine
-    from hyperbolic_optics_b200.plan import build_plan
-    from hyperbolic_optics_b200.scenario import ScenarioSetup
-
-    sc, payload = parity.scenario_for(name, ScenarioSetup)
-    plan = build_plan(sc, payload["Layers"])
-    prob = engine.DeviceProblem(plan, "scattering", "cuda:0")
-    n = plan.n_points
-    hi = engine.DeviceOutputs(n, prob.device)
-    lo = engine.DeviceOutputs(n, prob.device, dtype=torch.complex64)
-    engine.reflect(prob, hi)
-    engine.reflect(prob, lo)
-    torch.cuda.synchronize()
-    a = {k: hi.r[i].cpu().numpy() for i, k in enumerate(parity.R_KEYS)}
-    b = {k: lo.r[i].cpu().numpy().astype(np.complex128) for i, k in enumerate(parity.R_KEYS)}
-    err = parity.jones_error(b, a)
-    frac_ok = float((err <= parity.TOL_C64).mean())
-    assert frac_ok >= 0.999, f"{name}: only {frac_ok:.4f} of points within 1e-4 (max {np.nanmax(err):.2e})"
+@pytest.mark.parametrize("name", list(ALL))
+@pytest.mark.parametrize("backend", ["transfer", "scattering"])
+def test_complex64_path(name, backend, built_library):
+    """Opt-in complex64 arithmetic vs the REFERENCE (fixtures generated by the unmodified package):
+    e_J <= 1e-4 (north_star) at every point -- unmasked for the scattering backend; for the transfer
+    backend wherever the reference's own 2x2 block of Gamma has cond < 1e10 (beyond that the
+    transfer product is noise in any precision).  Measured: worst 2.1e-5; the only
+    points above 1e-4 sit at cond > 1e16."""
+    fx = parity.load_fixture(name)
+    s = _run_gpu(name, backend, precision="complex64")
+    assert np.asarray(s.r_pp).dtype == np.complex64
+    got = {k: parity.subsample(np.asarray(getattr(s, k)).astype(np.complex128), fx["strides"]) for k in parity.R_KEYS}
+    err = parity.jones_error(got, fx, "", "" if backend == "transfer" else "s_")
+    if backend == "scattering":
+        assert np.isfinite(err).all()
+        mask = np.ones(np.shape(err), dtype=bool)
+    else:
+        with np.errstate(all="ignore"):
+            mask = np.isfinite(err) & np.isfinite(fx["r_pp"]) & (fx["cond"] < 1e10)
+        assert mask.mean() >= 0.55      # 0.58 on the 11-layer stack (BASELINE names the scattering backend for it), >= 0.86 elsewhere
+    worst = float(np.max(err[mask])) if np.ndim(err) else float(err)
+    assert worst <= parity.TOL_C64, f"{name}/{backend}: complex64 max Jones rel err {worst:.3e}"
+    mu = parity.subsample(np.asarray(s.mueller).astype(np.float64), fx["strides"], 2)
+    ref_mu = fx["mueller"]
+    if backend == "transfer":
+        scale = np.maximum(np.abs(ref_mu).max(axis=(-1, -2)), 1e-300)
+        merr = np.abs(mu - ref_mu).max(axis=(-1, -2)) / scale
+        assert float(np.max(merr[mask])) <= 10 * parity.TOL_C64
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
