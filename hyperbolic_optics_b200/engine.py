@@ -190,11 +190,11 @@ class DeviceOutputs:
     """Caller-owned output buffers for a contiguous range of batch points."""
 
     def __init__(self, n, device, mueller=True, stokes=None, dtype=torch.complex128, power_planes=0,
-                 transmission=False):
+                 transmission=False, jones=True):
         self.n = n
         self.dtype = dtype
         real = torch.float64 if dtype == torch.complex128 else torch.float32
-        self.r = torch.empty((4, n), dtype=dtype, device=device)  # rows: pp, ps, sp, ss
+        self.r = torch.empty((4, n), dtype=dtype, device=device) if jones else None  # rows: pp, ps, sp, ss
         self.mueller = torch.empty((n, 4, 4), dtype=real, device=device) if mueller else None
         self.stokes = torch.empty((n, 4), dtype=real, device=device) if stokes is not None else None
         self.incident_stokes = stokes
@@ -205,10 +205,20 @@ class DeviceOutputs:
         # mode-resolved transmittance planes: (p inc, s-like mode), (p, p-like), (s, s-like), (s, p-like)
         self.t_mode = torch.empty((4, n), dtype=real, device=device) if transmission else None
 
+    @classmethod
+    def view(cls, r_rows, mueller=None):
+        """Outputs that point INTO existing buffers: ``r_rows`` a ``[4, n]`` view whose rows are
+        contiguous (e.g. ``full_r[:, lo:hi]``), ``mueller`` a contiguous ``[n, 4, 4]`` slice."""
+        self = object.__new__(cls)
+        self.n, self.dtype = int(r_rows.shape[1]), r_rows.dtype
+        self.r, self.mueller = r_rows, mueller
+        self.stokes = self.incident_stokes = self.power = self.t = self.t_mode = None
+        return self
+
     @property
     def nbytes(self):
-        total = self.r.numel() * self.r.element_size()
-        for t in (self.mueller, self.stokes, self.power, self.t, self.t_mode):
+        total = 0
+        for t in (self.r, self.mueller, self.stokes, self.power, self.t, self.t_mode):
             if t is not None:
                 total += t.numel() * t.element_size()
         return total
@@ -217,8 +227,8 @@ class DeviceOutputs:
 def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None, select="all"):
     """Launch the fused kernel for points ``[n_begin, n_end)`` into ``out`` (asynchronous).
 
-    ``select``: "all" fills every buffer ``out`` holds; "power" only the power planes,
-    "no-power" everything else (used to take the power bookkeeping from the stable recursion
+    ``select``: "all" fills every buffer ``out`` holds; "mueller" only the Mueller matrix (and the
+    Stokes vector); "power" only the power planes, "no-power" everything else (used to take the power bookkeeping from the stable recursion
     while r_ij / t_ij keep transfer-matrix semantics)."""
     n_end = problem.n_points if n_end is None else n_end
     if n_end - n_begin > out.n:
@@ -228,24 +238,26 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
     if out.dtype == torch.complex128:
         o = nat.Outputs()
         if select != "power":
-            o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
+            if out.r is not None and select != "mueller":
+                o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
             o.mueller = out.mueller.data_ptr() if out.mueller is not None else None
             o.stokes = out.stokes.data_ptr() if out.stokes is not None else None
             if out.incident_stokes is not None:
                 o.incident_stokes = (C.c_double * 4)(*[float(x) for x in out.incident_stokes])
-        if out.power is not None and select != "no-power":
+        if out.power is not None and select not in ("no-power", "mueller"):
             per = len(problem.plan.layers) + 1
             if out.power.shape[0] not in (2 * per, 4 * per):
                 raise ValueError("power buffer must have 2 or 4 times (n_layers + 1) planes")
             o.power, o.power_stride = out.power.data_ptr(), out.power.shape[1]
             o.power_states = out.power.shape[0] // per
-        if out.t is not None and select != "power":
+        if out.t is not None and select not in ("power", "mueller"):
             o.t_pp, o.t_ps, o.t_sp, o.t_ss = (out.t[i].data_ptr() for i in range(4))
             o.t_mode, o.t_mode_stride = out.t_mode.data_ptr(), out.t_mode.shape[1]
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:
         o = nat.OutputsF32()
-        o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
+        if out.r is not None and select != "mueller":
+            o.r_pp, o.r_ps, o.r_sp, o.r_ss = (out.r[i].data_ptr() for i in range(4))
         o.mueller = out.mueller.data_ptr() if out.mueller is not None else None
         nat.check(lib.ho_reflect_f32(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
 

@@ -114,6 +114,24 @@ def run(planes: JonesPlanes, want, s_pre=None, m_post=None, e_pre=None, j_post=N
     return shaped
 
 
+def mueller_into(rows, out, stream=None):
+    """``out[n, 4, 4]`` (contiguous device float64) <- Mueller matrices of the four contiguous
+    complex128 device vectors ``rows`` = (pp, ps, sp, ss); one ``ho_polarimetry`` pass, 64 B read +
+    128 B written per point (reference ``mueller.py:256-325``)."""
+    n = int(rows[0].numel())
+    if n == 0:
+        return
+    req = nat.Polarimetry()
+    req.j_pp, req.j_ps, req.j_sp, req.j_ss = (t.data_ptr() for t in rows)
+    req.s_pre = (C.c_double * 4)(1.0, 0.0, 0.0, 0.0)
+    req.m_post = (C.c_double * 16)(*np.eye(4).reshape(16))
+    req.e_pre = (nat.c128 * 2)(_c128(1.0), _c128(0.0))
+    req.j_post = (nat.c128 * 4)(_c128(1.0), _c128(0.0), _c128(0.0), _c128(1.0))
+    req.mueller = out.data_ptr()
+    handle = (stream or torch.cuda.current_stream(out.device)).cuda_stream
+    nat.check(nat.lib().ho_polarimetry(C.byref(req), n, handle))
+
+
 def deliver(t, on_device):
     """Results follow the structure: device tensors for ``keep_on_device`` runs, NumPy otherwise."""
     return t if on_device else t.cpu().numpy()

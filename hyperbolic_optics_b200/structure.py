@@ -15,7 +15,8 @@ error: the transfer backend returns inf/NaN where the reference's 4x4 product ov
 Additions (all optional): ``shard=(rank, world_size)`` (one process per GPU: this process
 computes -- and returns -- only its contiguous slab of the slowest swept axis, ``sharding.py``),
 ``precision="complex64"`` (opt-in single-precision kernels, 1e-4; r_ij + Mueller only),
-``mueller`` (the sample Mueller matrix, fused into the same kernel), ``stokes`` for a given incident Stokes vector, ``power=True`` (R, T and layer-resolved
+``mueller`` (the sample Mueller matrix, fused into the same kernel; ``"lazy"``: produced on first
+access of ``structure.mueller``), ``stokes`` for a given incident Stokes vector, ``power=True`` (R, T and layer-resolved
 absorption for p and s incidence from the same launch, both backends; consumed by
 ``hyperbolic_optics_b200.FieldProfile``), ``device=`` / ``keep_on_device=``.
 
@@ -30,6 +31,8 @@ canonical ``[A, B, F, T, 4, 4]`` arrays.
 
 from __future__ import annotations
 
+import sys
+
 import numpy as np
 import torch
 
@@ -38,19 +41,59 @@ from .plan import StackPlan, build_plan
 from .scenario import ScenarioSetup, present
 from .waves import LayerRecord, WaveProfile, iso_exit_matrix, prism_matrix
 
-_PINNED_POOL = {}
+def _storage_users(t):
+    """How many owners the tensor's storage has (tensor objects, views, NumPy arrays made by
+    ``.numpy()`` -- which keep a detached alias of the tensor alive as their ``base``)."""
+    return torch._C._storage_Use_Count(t.untyped_storage()._cdata)
 
 
-def _pinned(name, shape, dtype):
-    """Reusable pinned host buffers (allocation of GBs of page-locked memory is slow)."""
-    key = (name, tuple(shape), dtype)
-    buf = _PINNED_POOL.get(key)
-    if buf is None:
-        for k in [k for k in _PINNED_POOL if k[0] == name]:
-            del _PINNED_POOL[k]
-        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
-        _PINNED_POOL[key] = buf
-    return buf
+class _PinnedPool:
+    """Page-locked result buffers, LEASED to the NumPy arrays a run returns.
+
+    Page-locking gigabytes is slow (seconds for the 19 GB of a 1e8-point sweep), so buffers are
+    reused -- but never while somebody still looks at them: every result array is a NumPy view
+    whose ``base`` chain ends in an alias of the buffer's tensor, i.e. one more owner of its
+    storage, so the storage's use count tells whether any result (or slice of one) of an earlier
+    run is still alive.  A live buffer is left alone and a new one is allocated; a buffer whose
+    arrays have all been dropped is handed out again.  Results are therefore private to their
+    ``Structure`` (drop-in semantics) without the extra host copy that used to cost more than the
+    whole D2H transfer."""
+
+    def __init__(self, allocate=None):
+        self._bufs = {}     # key -> list of (tensor, idle use count)
+        self._allocate = allocate or (lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True))
+
+    @staticmethod
+    def _idle(entry):
+        try:
+            return _storage_users(entry[0]) <= entry[1]
+        except Exception:  # noqa: BLE001 - private torch API missing: never recycle (correct, just slower)
+            return False
+
+    def lease(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        bufs = self._bufs.setdefault(key, [])
+        for entry in bufs:
+            if self._idle(entry):
+                return entry[0]
+        # nothing free: drop idle buffers of other shapes under this name before growing
+        for other in [k for k in self._bufs if k[0] == name and k != key]:
+            self._bufs[other] = [e for e in self._bufs[other] if not self._idle(e)]
+            if not self._bufs[other]:
+                del self._bufs[other]
+        t = self._allocate(tuple(shape), dtype)
+        try:
+            idle = _storage_users(t)
+        except Exception:  # noqa: BLE001
+            idle = -1
+        bufs.append((t, idle))
+        return t
+
+    def n_buffers(self):
+        return sum(len(v) for v in self._bufs.values())
+
+
+_PINNED = _PinnedPool()
 
 
 class Structure:
@@ -69,7 +112,7 @@ class Structure:
         self.t_pp = self.t_ss = self.t_ps = self.t_sp = None
         self.mode_transmittance = None
         self._gamma = None
-        self.mueller = None
+        self._mueller = None
         self.stokes = None
         self.plan: StackPlan | None = None
         self.problem = None   # engine.DeviceProblem of the last run
@@ -88,8 +131,9 @@ class Structure:
         self.power = None
         self.incident_stokes = None
         self.keep_on_device = False
-        # True: results are private NumPy copies (drop-in semantics).  False: zero-copy views of
-        # the reusable pinned staging buffers, valid until the next run of the same shape.
+        # Host results are NumPy views of page-locked buffers leased from _PinnedPool: private to this
+        # Structure for as long as any of them is referenced, recycled afterwards (no extra host copy).
+        # (own_results is kept for callers of the earlier API; both settings behave like that now.)
         self.own_results = True
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -210,7 +254,7 @@ class Structure:
                 precision="complex128"):
         if backend not in ("transfer", "scattering"):
             raise ValueError(f"Unknown backend {backend!r}; use 'transfer' or 'scattering'.")
-        self.with_mueller = bool(mueller)
+        self.with_mueller = "lazy" if mueller == "lazy" else bool(mueller)
         self.with_power = bool(power)
         self.power_states = 4 if power == "full" else 2
         self.with_transmission = bool(transmission)
@@ -234,7 +278,22 @@ class Structure:
         self._run(backend)
 
     # -- device run ------------------------------------------------------------------------
-    def _run(self, backend):
+    @property
+    def mueller(self):
+        """Sample Mueller matrix ``[..., 4, 4]`` (reference ``mueller.py:256-325``).  With
+        ``execute(..., mueller="lazy")`` it is produced on first access: the kernel is re-launched
+        on the kept plan with only the Mueller output enabled (recomputing is cheaper than moving
+        ``r_ij`` back to the device: 11 ms per 1e8 points), so a run whose consumer only needs
+        ``r_ij`` moves 64 instead of 192 B per point over PCIe."""
+        if self._mueller is None and self.with_mueller == "lazy" and self.plan is not None and self.r_pp is not None:
+            self._run(self._last_backend, only_mueller=True)
+        return self._mueller
+
+    @mueller.setter
+    def mueller(self, value):
+        self._mueller = value
+
+    def _run(self, backend, only_mueller=False):
         self._last_backend = backend
         plan = self.plan
         prob = engine.DeviceProblem(plan, backend, self.device, device_tables=self.device_tables, protocol=self.protocol,
@@ -245,11 +304,13 @@ class Structure:
         # R, T, A_i are backend-independent physics; they always come from the stable recursion,
         # which stays accurate where the transfer product is ill conditioned (two forward modes of a
         # film growing at very different rates) or overflows.  r_ij, t_ij keep the requested semantics.
-        split_power = self.with_power and backend == "transfer"
+        split_power = self.with_power and backend == "transfer" and not only_mueller
         prob_power = prob.with_backend("scattering") if split_power else None
 
         def launch(buf, lo, hi, stream=None):
-            if split_power:
+            if only_mueller:
+                engine.reflect(prob, buf, lo, hi, stream=stream, select="mueller")
+            elif split_power:
                 engine.reflect(prob, buf, lo, hi, stream=stream, select="no-power")
                 engine.reflect(prob_power, buf, lo, hi, stream=stream, select="power")
             else:
@@ -264,28 +325,38 @@ class Structure:
         self.point_range = (base, base + n)
         if n == 0:
             raise ValueError(f"shard {self.shard}: more ranks than samples of the sharded axis")
-        want_stokes = self.incident_stokes is not None
-        planes = self.power_states * (len(plan.layers) + 1) if self.with_power else 0
+        eager_mueller = only_mueller or self.with_mueller is True
+        want_stokes = self.incident_stokes is not None and not only_mueller
+        planes = self.power_states * (len(plan.layers) + 1) if (self.with_power and not only_mueller) else 0
+        transmission = self.with_transmission and not only_mueller
         cdtype = torch.complex64 if self.precision == "complex64" else torch.complex128
         rdtype = torch.float32 if self.precision == "complex64" else torch.float64
         if self.keep_on_device:
-            out = engine.DeviceOutputs(n, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
-                                       transmission=self.with_transmission, dtype=cdtype)
+            out = engine.DeviceOutputs(n, prob.device, eager_mueller, self.incident_stokes if want_stokes else None,
+                                       power_planes=planes, transmission=transmission, dtype=cdtype, jones=not only_mueller)
             launch(out, base, base + n)
-            r = out.r.reshape((4,) + shape)
-            self._assign(r, out.mueller, out.stokes, out.power, out.t, shape, to_numpy=False, tmode=out.t_mode)
+            if only_mueller:
+                self._mueller = _present_torch(out.mueller.reshape(shape + (4, 4)))
+                return
+            self._assign(out.r.reshape((4,) + shape), out.mueller, out.stokes, out.power, out.t, shape, tmode=out.t_mode)
             self.d2h_bytes = 0
             return
-        # host results: kernel -> device chunk (double buffered) -> pinned host, D2H on a copy stream
+        # host results: kernel -> device chunk (double buffered) -> leased pinned host buffers, D2H on a copy stream
         chunk = min(n, self.chunk_points)
-        host_r = _pinned("r", (4, n), cdtype)
-        host_m = _pinned("m", (n, 4, 4), rdtype) if self.with_mueller else None
-        host_s = _pinned("s", (n, 4), torch.float64) if want_stokes else None
-        host_p = _pinned("p", (planes, n), torch.float64) if planes else None
-        host_t = _pinned("t", (4, n), torch.complex128) if self.with_transmission else None
-        host_tm = _pinned("tm", (4, n), torch.float64) if self.with_transmission else None
-        bufs = [engine.DeviceOutputs(chunk, prob.device, self.with_mueller, self.incident_stokes, power_planes=planes,
-                                     transmission=self.with_transmission, dtype=cdtype)
+        host = {}
+        if not only_mueller:
+            host["r"] = _PINNED.lease("r", (4, n), cdtype)
+        if eager_mueller:
+            host["m"] = _PINNED.lease("m", (n, 4, 4), rdtype)
+        if want_stokes:
+            host["s"] = _PINNED.lease("s", (n, 4), torch.float64)
+        if planes:
+            host["p"] = _PINNED.lease("p", (planes, n), torch.float64)
+        if transmission:
+            host["t"] = _PINNED.lease("t", (4, n), torch.complex128)
+            host["tm"] = _PINNED.lease("tm", (4, n), torch.float64)
+        bufs = [engine.DeviceOutputs(chunk, prob.device, eager_mueller, self.incident_stokes if want_stokes else None,
+                                     power_planes=planes, transmission=transmission, dtype=cdtype, jones=not only_mueller)
                 for _ in range(2 if n > chunk else 1)]
         compute = torch.cuda.current_stream(prob.device)
         copy = torch.cuda.Stream(prob.device)
@@ -301,45 +372,51 @@ class Structure:
             copy.wait_event(ready)
             with torch.cuda.stream(copy):
                 m = stop - start
-                for i in range(4):  # contiguous row slices -> plain cudaMemcpyAsync each
-                    host_r[i, start:stop].copy_(buf.r[i, :m], non_blocking=True)
-                if host_m is not None:
-                    host_m[start:stop].copy_(buf.mueller[:m], non_blocking=True)
-                if host_s is not None:
-                    host_s[start:stop].copy_(buf.stokes[:m], non_blocking=True)
+                if "r" in host:
+                    for i in range(4):  # contiguous row slices -> plain cudaMemcpyAsync each
+                        host["r"][i, start:stop].copy_(buf.r[i, :m], non_blocking=True)
+                if "m" in host:
+                    host["m"][start:stop].copy_(buf.mueller[:m], non_blocking=True)
+                if "s" in host:
+                    host["s"][start:stop].copy_(buf.stokes[:m], non_blocking=True)
                 for i in range(planes):
-                    host_p[i, start:stop].copy_(buf.power[i, :m], non_blocking=True)
-                if host_t is not None:
+                    host["p"][i, start:stop].copy_(buf.power[i, :m], non_blocking=True)
+                if "t" in host:
                     for i in range(4):
-                        host_t[i, start:stop].copy_(buf.t[i, :m], non_blocking=True)
-                        host_tm[i, start:stop].copy_(buf.t_mode[i, :m], non_blocking=True)
+                        host["t"][i, start:stop].copy_(buf.t[i, :m], non_blocking=True)
+                        host["tm"][i, start:stop].copy_(buf.t_mode[i, :m], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             done[ci % len(bufs)] = ev
         copy.synchronize()
         scale = 2 if self.precision == "complex128" else 1
-        self.d2h_bytes = n * ((32 + (64 if host_m is not None else 0)) * scale
-                              + (32 if host_s is not None else 0) + 8 * planes + (96 if host_t is not None else 0))
-        self._assign(host_r.reshape((4,) + shape), host_m, host_s, host_p, host_t, shape, to_numpy=True, tmode=host_tm)
+        moved = n * ((32 if "r" in host else 0) + (64 if "m" in host else 0)) * scale \
+            + n * ((32 if "s" in host else 0) + 8 * planes + (96 if "t" in host else 0))
+        # NumPy views whose base chain ends in the leased tensor objects (see _PinnedPool)
+        arr = {k: t.numpy() for k, t in host.items()}
+        del host
+        if only_mueller:
+            self.d2h_bytes += moved
+            self._mueller = present(arr["m"].reshape(shape + (4, 4)))
+            return
+        self.d2h_bytes = moved
+        self._assign(arr["r"].reshape((4,) + shape), arr.get("m"), arr.get("s"), arr.get("p"), arr.get("t"), shape,
+                     tmode=arr.get("tm"))
 
-    def _assign(self, r, mueller, stokes, power, trans, shape, to_numpy, tmode=None):
-        if to_numpy:
-            conv = (lambda t: np.array(t.numpy())) if self.own_results else (lambda t: t.numpy())
-        else:
-            conv = lambda t: t
-        pres = present if to_numpy else _present_torch
-        self.r_pp, self.r_ps, self.r_sp, self.r_ss = (pres(conv(r[i])) for i in range(4))
-        self.mueller = pres(conv(mueller.reshape(shape + (4, 4)))) if mueller is not None else None
-        self.stokes = pres(conv(stokes.reshape(shape + (4,)))) if stokes is not None else None
+    def _assign(self, r, mueller, stokes, power, trans, shape, tmode=None):
+        pres = _present_torch if isinstance(r, torch.Tensor) else present
+        self.r_pp, self.r_ps, self.r_sp, self.r_ss = (pres(r[i]) for i in range(4))
+        self._mueller = pres(mueller.reshape(shape + (4, 4))) if mueller is not None else None
+        self.stokes = pres(stokes.reshape(shape + (4,))) if stokes is not None else None
         if trans is not None:
             t4 = trans.reshape((4,) + shape)
-            self.t_pp, self.t_ps, self.t_sp, self.t_ss = (pres(conv(t4[i])) for i in range(4))
+            self.t_pp, self.t_ps, self.t_sp, self.t_ss = (pres(t4[i]) for i in range(4))
         else:
             self.t_pp = self.t_ps = self.t_sp = self.t_ss = None
         # per incidence ("p", "s"): transmittance carried by the s-like and the p-like exit mode
         self.mode_transmittance = None
         if tmode is not None:
-            tm = [pres(conv(tmode[i].reshape(shape))) for i in range(4)]
+            tm = [pres(tmode[i].reshape(shape)) for i in range(4)]
             self.mode_transmittance = {"p": {"s": tm[0], "p": tm[1]}, "s": {"s": tm[2], "p": tm[3]}}
         self.power = None
         if power is not None:
@@ -348,7 +425,7 @@ class Structure:
             per = len(self.plan.layers) + 1
             self.power = {}
             for pi, pol in enumerate("psdc"[:power.shape[0] // per]):
-                blk = [pres(conv(power[pi * per + k].reshape(shape))) for k in range(per)]
+                blk = [pres(power[pi * per + k].reshape(shape)) for k in range(per)]
                 self.power[pol] = {"R": blk[0], "T": blk[1], "A": blk[2:]}
 
 

@@ -11,6 +11,8 @@ is computed for callers that only read ``r_ij``.
 
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from . import plan as P
@@ -50,7 +52,9 @@ class LayerRecord:
     ``profile`` attribute at all, which is what the reference's consumers test for."""
 
     def __init__(self, owner, index, layer_plan=None):
-        self._owner, self._index, self.plan = owner, index, layer_plan   # index 0 = prism
+        # weak: structure.layers -> record -> structure would be a cycle, and a Structure must die by
+        # reference count so that its leased result buffers return to the pool at once
+        self._owner_ref, self._index, self.plan = weakref.ref(owner), index, layer_plan   # index 0 = prism
         self._matrix = None
         self._profile = None
         if layer_plan is None:
@@ -65,17 +69,23 @@ class LayerRecord:
             for name in ("kind", "eps", "mu", "mu_scalar", "eps_scalar", "cos_beta", "sin_beta", "material", "rotation_xy"):
                 setattr(self, name, getattr(layer_plan, name))
 
+    def _owner(self):
+        owner = self._owner_ref()
+        if owner is None:
+            raise ReferenceError("the Structure this layer belongs to no longer exists")
+        return owner
+
     @property
     def matrix(self):
         if self._matrix is None:
-            self._owner._materialise_layer(self)
+            self._owner()._materialise_layer(self)
         return self._matrix
 
     def __getattr__(self, name):
         # `profile` only exists on Wave-built layers (getattr(layer, "profile", None) in the reference)
         if name == "profile" and self.plan is not None and self.plan.kind != P.KIND_ISO_EXIT:
             if self._profile is None:
-                self._owner._materialise_layer(self)
+                self._owner()._materialise_layer(self)
             return self._profile
         raise AttributeError(name)
 

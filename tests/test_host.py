@@ -265,3 +265,51 @@ def test_fast_path_hint_and_scalar_detection():
                      {"type": "Semi Infinite Isotropic Layer", "permittivity": 2.0}],
                     {"type": "Incident", "frequency": [900.0, 1000.0]})
     assert iso.fast_path
+
+
+def test_result_buffers_are_leased_not_overwritten():
+    """Host results are views of pooled page-locked buffers; the pool must never hand a buffer out
+    again while a result array (or any slice of one) of an earlier run is still referenced."""
+    import torch
+
+    from hyperbolic_optics_b200.structure import _PinnedPool
+
+    pool = _PinnedPool(allocate=lambda shape, dtype: torch.empty(shape, dtype=dtype))   # (pageable here: no GPU)
+    first = pool.lease("r", (4, 10), torch.complex128)
+    ptr = first.data_ptr()
+    piece = first.numpy().reshape(4, 2, 5)[1]          # what Structure hands to the caller
+    del first
+    second = pool.lease("r", (4, 10), torch.complex128)
+    assert second.data_ptr() != ptr and pool.n_buffers() == 2      # first still referenced through `piece`
+    piece[...] = 7.0
+    del second
+    del piece
+    third = pool.lease("r", (4, 10), torch.complex128)
+    assert third.data_ptr() == ptr and pool.n_buffers() == 2       # released -> recycled
+    held = third.numpy()
+    other = pool.lease("r", (4, 20), torch.complex128)              # new shape: idle buffers of the old one are dropped
+    assert pool.n_buffers() == 2 and held.shape == (4, 10)
+    del other, third
+
+
+def test_structure_dies_by_reference_count():
+    """No reference cycle through structure.layers: dropping a Structure must release its (leased,
+    page-locked) result buffers immediately, not at the next garbage collection."""
+    import gc
+    import weakref
+
+    from hyperbolic_optics_b200 import Structure
+
+    gc.disable()
+    try:
+        s = Structure()
+        s.get_scenario({"type": "Incident", "frequency": [1000.0]})
+        s.get_layers([{"type": "Ambient Incident Layer", "permittivity": 12.5},
+                      {"type": "Semi Infinite Isotropic Layer", "permittivity": 2.0}])
+        assert s.layers[0].matrix.shape == (360, 1, 1, 1, 4, 4) and s.layers[1].matrix.shape == (360, 1, 1, 1, 4, 4)
+        assert getattr(s.layers[1], "profile", None) is None and s.transfer_matrix is None
+        alive = weakref.ref(s)
+        del s
+        assert alive() is None
+    finally:
+        gc.enable()

@@ -79,3 +79,42 @@ def test_gloo_world2_gather_equals_single_process(name, tmp_path):
         assert ok == "True"
         total += int(n)
     assert total == plan.n_points
+
+
+@pytest.mark.parametrize("lo,hi,n_chunks", [(0, 100, 8), (17, 23, 8), (5, 5, 3), (0, 7, 7)])
+def test_chunk_ranges_tile_a_slab(lo, hi, n_chunks):
+    spans = [sharding.chunk_range(lo, hi, c, n_chunks) for c in range(n_chunks)]
+    assert spans[0][0] == lo and spans[-1][1] == hi
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(n_chunks - 1))
+
+
+def _exchange_worker(rank, world, port, name, n_chunks, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = _plan(name)
+        n = plan.n_points
+        ranges = [sharding.point_range(plan, world, r) for r in range(world)]
+        truth = [torch.arange(n, dtype=torch.float64) * (k + 1) + 0.25 * k for k in range(3)]
+        truth.append(torch.complex(truth[0], -truth[1]))      # a complex plane, like r_ij
+        rows = [torch.full_like(t, float("nan")) for t in truth]
+        lo, hi = ranges[rank]
+        for c in range(n_chunks):                              # "compute" chunk c of my slab, then exchange it
+            a, b = sharding.chunk_range(lo, hi, c, n_chunks)
+            for row, t in zip(rows, truth):
+                row[a:b] = t[a:b]
+            for work in sharding.exchange_chunk(rows, ranges, c, n_chunks, rank):
+                work.wait()
+        ok = all(torch.equal(row, t) for row, t in zip(rows, truth))
+        Path(out_dir, f"rank{rank}.txt").write_text(str(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_chunks", [(2, 4), (3, 5)])
+def test_gloo_pipelined_exchange_places_every_chunk(world, n_chunks, tmp_path):
+    """The all-gather step of ``GatheredSweep`` (point-to-point, chunk by chunk, unequal slabs):
+    after the last chunk every rank holds the whole presentation-ordered planes."""
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_exchange_worker, args=(world, port, "c4_fullsweep_hbn_sic", n_chunks, str(tmp_path)), nprocs=world, join=True)
+    assert all(Path(tmp_path, f"rank{r}.txt").read_text() == "True" for r in range(world))

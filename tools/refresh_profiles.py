@@ -1,40 +1,61 @@
-"""Copy one round's GPU evidence from gpurun_out/ into profiles/ (run in the build container).
+"""Turn one ncu --set full capture (gpurun_out/<name>.ncu-rep, made with `-k regex:<kernel> -c <n>`
+over ONE step of `bench.py`-like work) into the tracked evidence under profiles/ and, for bench
+workloads, into `profiles/ncu_constants.json` (run in the build container, no GPU needed).
 
-    python tools/refresh_profiles.py v13 10076160
+    python tools/refresh_profiles.py <report stem> <out tag> <points per step> [--workload c4]
+
+Writes profiles/<tag>_full.{md,json} (summary over ALL captured launches: the fast-path launch and
+its fix-up pass together make one step), profiles/<tag>_sass_histogram.txt, and -- with
+--workload -- the per-point constants bench.py reads, keyed by the sha256 of csrc/ + the header so
+that a later kernel change makes them stale instead of silently wrong.
 """
+import argparse
 import json
 import subprocess
 import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-tag, points = sys.argv[1], int(sys.argv[2])
-g, p = ROOT / "gpurun_out", ROOT / "profiles"
-pre = f"r01_{tag}"
-subprocess.run([sys.executable, str(ROOT / "tools/summarize_ncu.py"), str(g / f"prof_{tag}.ncu-rep"),
-                str(p / f"{pre}_reflect_kernel_full"), str(points)], check=True, stdout=subprocess.DEVNULL)
-src = subprocess.run(["ncu", "-i", str(g / f"prof_{tag}.ncu-rep"), "--page", "source", "--csv"],
-                     capture_output=True, text=True).stdout
-(g / f"prof_{tag}_source.csv").write_text(src)
-hist = subprocess.run([sys.executable, str(ROOT / "tools/ncu_sass_hist.py"), str(g / f"prof_{tag}_source.csv")],
-                      capture_output=True, text=True).stdout
-(p / f"{pre}_sass_histogram.txt").write_text(hist)
-for src_name, dst_name in ((f"bench_{tag}_default.log", f"{pre}_bench_default.json"),
-                           (f"bench_{tag}_reference.log", f"{pre}_bench_reference_arm.json")):
-    if (g / src_name).exists():
-        lines = [l for l in (g / src_name).read_text().splitlines() if l.startswith("{")]
-        (p / dst_name).write_text(lines[-1] + "\n")
-for src_name, dst_name in ((f"launches_{tag}.csv", f"{pre}_launches_bench.csv"),
-                           (f"config_bench_{tag}.jsonl", f"r01_config_bench_{tag}.jsonl"),
-                           (f"config_bench_{tag}_c64.jsonl", f"r01_config_bench_{tag}_c64.jsonl")):
-    if (g / src_name).exists():
-        (p / dst_name).write_text((g / src_name).read_text())
-d = json.load(open(p / f"{pre}_reflect_kernel_full.json"))
-dd, l0 = d["derived"], d["launches"][0]
-const = {"source": f"profiles/{pre}_reflect_kernel_full.md (ncu --set full, one launch of {points} C4 points, kernel {tag})",
-         "dram_bytes_per_point": dd["dram_bytes_per_point"],
-         "executed_fp64_flop_per_point": dd["executed_fp64_flop_per_point"],
-         "fp64_thread_inst_per_point": dd["fp64_thread_inst_per_point"],
-         "fp64_pipe_active_pct": float(l0["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]["value"])}
-json.dump(const, open(p / "ncu_constants.json", "w"), indent=1)
-print(json.dumps(const, indent=1))
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("stem")
+    ap.add_argument("tag")
+    ap.add_argument("points", type=int)
+    ap.add_argument("--workload", default="")
+    args = ap.parse_args()
+    g, p = ROOT / "gpurun_out", ROOT / "profiles"
+    rep = g / f"{args.stem}.ncu-rep"
+    subprocess.run([sys.executable, str(ROOT / "tools/summarize_ncu.py"), str(rep), str(p / f"{args.tag}_full"), str(args.points)],
+                   check=True, stdout=subprocess.DEVNULL)
+    src = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    (g / f"{args.stem}_source.csv").write_text(src)
+    hist = subprocess.run([sys.executable, str(ROOT / "tools/ncu_sass_hist.py"), str(g / f"{args.stem}_source.csv")],
+                          capture_output=True, text=True).stdout
+    (p / f"{args.tag}_sass_histogram.txt").write_text(hist)
+    d = json.load(open(p / f"{args.tag}_full.json"))
+    print(json.dumps(d["derived"], indent=1))
+    if args.workload:
+        import bench
+
+        path = p / "ncu_constants.json"
+        table = json.loads(path.read_text()) if path.exists() else {}
+        if "executed_fp64_flop_per_point" in table:   # round-1 layout (flat, C4 only)
+            table = {}
+        dd = d["derived"]
+        table[args.workload] = {
+            "source": f"profiles/{args.tag}_full.md (ncu --set full, {len(d['launches'])} launch(es) = one step of {args.points} points)",
+            "csrc_sha256": bench.library_fingerprint(),
+            "dram_bytes_per_point": dd["dram_bytes_per_point"],
+            "executed_fp64_flop_per_point": dd["executed_fp64_flop_per_point"],
+            "fp64_thread_inst_per_point": dd["fp64_thread_inst_per_point"],
+            "fp64_pipe_active_pct": dd["fp64_pipe_active_pct_main_launch"],
+        }
+        path.write_text(json.dumps(table, indent=1) + "\n")
+        print(json.dumps(table[args.workload], indent=1))
+
+
+if __name__ == "__main__":
+    main()
