@@ -381,7 +381,8 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---- STRONG scaling with the final all-gather over NVLink inside the timed region ----
     gathered = None
     if world > 1 and not args.no_gather:
-        sweep = sharding.GatheredSweep(plan, "transfer", device, world, rank, n_chunks=args.gather_chunks, mueller=True)
+        sweep = sharding.GatheredSweep(plan, "transfer", device, world, rank, n_chunks=args.gather_chunks, mueller=not args.gather_no_mueller,
+                                       transport=args.gather_transport, ctas_per_sm=args.gather_ctas_per_sm)
         g_ms, _ = timed(lambda: sweep.run(stream), args.steps, args.warmup)
         # correctness of the gathered result: every rank checks a foreign slab against a direct evaluation
         peer = (rank + 1) % world
@@ -389,16 +390,25 @@ def run_b200_arm(args, rank, local_rank, world):
         probe = engine.DeviceOutputs(p_hi - p_lo, device, mueller=True)
         engine.reflect(engine.DeviceProblem(plan, "transfer", device, max_launch_points=p_hi - p_lo), probe, p_lo, p_hi, stream)
         torch.cuda.synchronize()
-        same = bool(torch.equal(probe.r, sweep.r[:, p_lo:p_hi])) and \
-            float((probe.mueller - sweep.mueller[p_lo:p_hi]).abs().max().item()) <= 1e-12
+        # (chunked launches may take another kernel build than the probe: agreement, not bit equality)
+        same = float((probe.r - sweep.r[:, p_lo:p_hi]).abs().max().item()) <= 1e-11 and \
+            (sweep.mueller is None or float((probe.mueller - sweep.mueller[p_lo:p_hi]).abs().max().item()) <= 1e-11)
         ok = torch.tensor([1.0 if same else 0.0], device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         recv = sweep.bytes_received
         gathered = {
             "value": n_total / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms, "chunks": sweep.n_chunks,
-            "what": "all-gather of the four r_ij planes (64 B/point) point-to-point over NVLink, chunk-pipelined behind "
-                    "compute on a second stream; the Mueller planes (128 B/point) are rebuilt on every rank from the "
-                    "received r_ij by ho_polarimetry (HBM is 7x an NVLink port) instead of being sent",
+            "transport": sweep.transport, "transport_error": sweep.transport_error,
+            "what": ("all-gather FUSED into the reflection kernel: every r_ij (64 B/point) is also stored into the peers' result "
+                     "buffers (symmetric memory over NVSwitch), overlapping the arithmetic inside one kernel"
+                     if sweep.transport == "fused" else
+                     "all-gather by the copy engines: each computed chunk of the r_ij planes (64 B/point) is pushed into the peers' "
+                     "result buffers (symmetric memory over NVSwitch, one stream per peer) behind the next chunk's compute"
+                     if sweep.transport == "dma" else
+                     "all-gather of the four r_ij planes (64 B/point) by grouped ncclSend/ncclRecv, chunk-pipelined behind "
+                     "compute on a second stream") +
+                    "; the Mueller planes (128 B/point) are rebuilt on every rank from the received r_ij by ho_polarimetry "
+                    "(HBM is 7x an NVLink port) instead of being sent",
             "received_bytes_per_rank": recv, "GBps_received_per_rank": recv / (g_ms * 1e-3) / 1e9,
             "limiter": f"NVLink ingest per GPU: {recv / 1e9:.2f} GB per step at <= 900 GB/s is >= {recv / 900e9 * 1e3:.2f} ms; "
                        f"compute alone is {ms_per_step:.2f} ms -> the step is max(compute, exchange), not their sum",
@@ -546,7 +556,10 @@ def main():
     ap.add_argument("--n-inc", type=int, default=N_INC)
     ap.add_argument("--n-az", type=int, default=N_AZ)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--gather-chunks", type=int, default=8)
+    ap.add_argument("--gather-chunks", type=int, default=None)
+    ap.add_argument("--gather-transport", default="auto", choices=["auto", "fused", "dma", "p2p"])
+    ap.add_argument("--gather-ctas-per-sm", type=int, default=None)
+    ap.add_argument("--gather-no-mueller", action="store_true", help="diagnostic: gather r_ij only, do not rebuild the Mueller planes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the gathered strong-scaling measurement at N > 1")
     ap.add_argument("--no-weak", action="store_true", help="skip the informational weak-scaling measurement at N > 1")

@@ -11,7 +11,8 @@ import os
 from pathlib import Path
 
 HO_MAX_LAYERS = 24
-HO_ABI_VERSION = 11
+HO_MAX_PEERS = 15
+HO_ABI_VERSION = 12
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -37,7 +38,7 @@ class Problem(C.Structure):
     _fields_ = [
         ("A", C.c_int32), ("B", C.c_int32), ("F", C.c_int32), ("T", C.c_int32),
         ("n_layers", C.c_int32), ("backend", C.c_int32), ("hint_fast_path", C.c_int32),
-        ("protocol", C.c_int32), ("tsweep_groups", C.c_int32), ("reserved0", C.c_int32),
+        ("protocol", C.c_int32), ("tsweep_groups", C.c_int32), ("max_ctas_per_sm", C.c_int32),
         ("work", C.c_void_p), ("work_capacity", C.c_int64),
         ("kx", C.c_void_p), ("k0", C.c_void_p),
         ("prism_inv_cos", C.c_void_p), ("prism_inv_ncos", C.c_void_p),
@@ -55,6 +56,7 @@ class Outputs(C.Structure):
         ("t_pp", C.c_void_p), ("t_ps", C.c_void_p), ("t_sp", C.c_void_p), ("t_ss", C.c_void_p),
         ("t_mode", C.c_void_p), ("t_mode_stride", C.c_int64),
         ("power_states", C.c_int32),
+        ("n_peers", C.c_int32), ("peer_r", (C.c_void_p * 4) * HO_MAX_PEERS),
     ]
 
 

@@ -44,6 +44,8 @@ template <typename T> struct OutPtrs {
   ho::cx<T>* t_pp; ho::cx<T>* t_ps; ho::cx<T>* t_sp; ho::cx<T>* t_ss;
   T* t_mode; int64_t t_mode_stride;
   int power_states;  // 2: p, s; 4: + (p + s)/sqrt2, (p + i s)/sqrt2
+  int n_peers;       // fused all-gather: further destinations of r_ij (peer memory over NVLink)
+  ho::cx<T>* peer[HO_MAX_PEERS][4];
 };
 
 template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p) {
@@ -242,6 +244,15 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
   if (out.r_ps) st_stream(out.r_ps + o, r_ps);
   if (out.r_sp) st_stream(out.r_sp + o, r_sp);
   if (out.r_ss) st_stream(out.r_ss + o, r_ss);
+  // fused all-gather: the same four coefficients into every peer's result buffer (NVLink stores,
+  // 512 contiguous bytes per warp and plane), overlapping the next point's arithmetic
+#pragma unroll 1
+  for (int p = 0; p < out.n_peers; ++p) {
+    st_stream(out.peer[p][0] + o, r_pp);
+    st_stream(out.peer[p][1] + o, r_ps);
+    st_stream(out.peer[p][2] + o, r_sp);
+    st_stream(out.peer[p][3] + o, r_ss);
+  }
   if (out.mueller || out.stokes) {
     T M[16];
     mueller_from_jones(r_pp, r_ps, r_sp, r_ss, M);
@@ -517,6 +528,7 @@ int validate(const ho_problem_t* p, int64_t n_begin, int64_t n_end) {
     return fail(HO_ERR_BAD_ARGUMENT, "unknown launch protocol");
   if (p->protocol == HO_PROTOCOL_FAST_FIXUP && (!p->work || p->work_capacity < 0))
     return fail(HO_ERR_BAD_ARGUMENT, "HO_PROTOCOL_FAST_FIXUP needs a work list");
+  if (p->max_ctas_per_sm < 0) return fail(HO_ERR_BAD_ARGUMENT, "max_ctas_per_sm must be >= 0");
   if (p->tsweep_groups < -1 || p->tsweep_groups > 32) return fail(HO_ERR_BAD_ARGUMENT, "tsweep_groups must be -1, 0 or 1..32");
   const int64_t N = (int64_t)p->A * p->B * p->F * p->T;
   if (n_begin < 0 || n_end < n_begin || n_end > N) return fail(HO_ERR_BAD_ARGUMENT, "point range outside the grid");
@@ -591,8 +603,12 @@ Limits launch_limits(const void* kernel, int threads, size_t smem) {
   return lim;
 }
 
-int grid_for(int64_t n, const void* kernel) {
+int grid_for(int64_t n, const void* kernel, int max_ctas_per_sm = 0) {
   const Limits lim = launch_limits(kernel, kThreads, 0);
+  if (max_ctas_per_sm > 0) {  // one wave of that many CTAs per SM
+    int64_t want = (n + kThreads - 1) / kThreads, cap = (int64_t)lim.sms * (max_ctas_per_sm < lim.per_sm ? max_ctas_per_sm : lim.per_sm);
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  }
   // grid-stride over at most 32 waves of resident CTAs (measured on C1-C4 against 2, 8 and
   // "one point per thread": 32 is best or within 1 % for both recursions)
   int waves = 32;
@@ -641,7 +657,7 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
       return launch_tsweep<STABLE, NM, POWER>(p, out, n_begin, n_end, swept, stream);
   }
   const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, false>;
-  const int grid = grid_for(n_end - n_begin, kern);
+  const int grid = grid_for(n_end - n_begin, kern, p->max_ctas_per_sm);
   if constexpr (sizeof(T) == 8 && !POWER) {
     // (below ~4M points the second launch costs more than the leaner kernel saves)
     const int64_t n = n_end - n_begin;
@@ -653,7 +669,7 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
       const int64_t cap = p->work_capacity < (int64_t)0x7fffffff ? p->work_capacity : (int64_t)0x7fffffff;
       if (cudaMemsetAsync(p->work, 0, sizeof(unsigned), stream) != cudaSuccess)
         return fail(HO_ERR_CUDA, "work list reset failed: %s", cudaGetErrorString(cudaGetLastError()));
-      reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n, fast), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
+      reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
       reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, p->work, (unsigned)cap);
       g_launches.fetch_add(1);
       return 0;
@@ -718,6 +734,13 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
   if (o.t_mode && !o.t_pp) return fail(HO_ERR_BAD_ARGUMENT, "t_mode needs the t_pp .. t_ss outputs");
   if (o.t_mode && o.t_mode_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "t_mode_stride is smaller than the point range");
   if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
+  if (out->n_peers < 0 || out->n_peers > HO_MAX_PEERS) return fail(HO_ERR_BAD_ARGUMENT, "n_peers must be 0 .. HO_MAX_PEERS");
+  o.n_peers = out->n_peers;
+  for (int p = 0; p < o.n_peers; ++p)
+    for (int k = 0; k < 4; ++k) {
+      if (!out->peer_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "peer_r: NULL destination");
+      o.peer[p][k] = reinterpret_cast<ho::cx<double>*>(out->peer_r[p][k]);
+    }
   DeviceScope scope(problem->kx);
   if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;
@@ -743,6 +766,7 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.t_mode = nullptr;
   o.t_mode_stride = 0;
   o.power_states = 2;
+  o.n_peers = 0;
   DeviceScope scope(problem->kx);
   if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;

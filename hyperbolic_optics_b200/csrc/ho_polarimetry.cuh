@@ -75,6 +75,24 @@ __device__ __forceinline__ void store16(double* dst, const double m[16]) {
   for (int k = 0; k < 8; ++k) __stcs(d2 + k, make_double2(m[2 * k], m[2 * k + 1]));
 }
 
+// The same for a FULL warp holding 32 consecutive points: the 4 KB block is staged in shared memory
+// (rows of 17 doubles: conflict-free) and written as eight fully coalesced 512-byte warp stores.
+// The direct form above makes every warp store touch 32 different 128-byte lines with 16 bytes each
+// -- invisible while a kernel is FP64-bound, but it capped the HBM-bound epilogue at 0.60 of peak.
+constexpr int kStageRow = 17;
+__device__ __forceinline__ void store16_warp(double* warp_dst, const double m[16], double* stage, int lane) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) stage[lane * kStageRow + k] = m[k];
+  __syncwarp();
+  double2* d2 = reinterpret_cast<double2*>(warp_dst);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int flat = j * 32 + lane, p = flat >> 3, d = flat & 7;
+    __stcs(d2 + flat, make_double2(stage[p * kStageRow + 2 * d], stage[p * kStageRow + 2 * d + 1]));
+  }
+  __syncwarp();
+}
+
 // [[1, top^T], [left, sub]] -> 16 contiguous doubles
 __device__ __forceinline__ void store_assembled(double* dst, const double top[3], const double left[3], const double sub[9]) {
   const double m[16] = {1.0, top[0], top[1], top[2], left[0], sub[0], sub[1], sub[2],
@@ -170,6 +188,8 @@ polarimetry_kernel(const __grid_constant__ ho_polarimetry_t q, int64_t n) {
   using namespace ho;
   typedef cx<double> C;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  __shared__ double stage[kPolarThreads / 32][32 * kStageRow];
+  const int lane = threadIdx.x & 31;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const C pp = ldc<double>(q.j_pp + i), ps = ldc<double>(q.j_ps + i);
     const C sp = ldc<double>(q.j_sp + i), ss = ldc<double>(q.j_ss + i);
@@ -178,7 +198,8 @@ polarimetry_kernel(const __grid_constant__ ho_polarimetry_t q, int64_t n) {
       double M[16];
       mueller_from_jones(pp, ps, sp, ss, M);
       if (q.mueller) {
-        store16(q.mueller + 16 * i, M);
+        if (__activemask() == 0xffffffffu) store16_warp(q.mueller + 16 * (i - lane), M, stage[threadIdx.x >> 5], lane);
+        else store16(q.mueller + 16 * i, M);   // ragged last warp
       }
       if (q.stokes || q.polarisation) {
         double v[4], s[4];

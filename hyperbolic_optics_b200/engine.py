@@ -34,7 +34,7 @@ class DeviceProblem:
     """A ``StackPlan`` resident on one GPU plus the filled ``ho_problem_t`` descriptor."""
 
     def __init__(self, plan: P.StackPlan, backend="transfer", device=None, device_tables=False, protocol="auto",
-                 work_capacity=None, tsweep_groups=0, max_launch_points=None):
+                 work_capacity=None, tsweep_groups=0, max_launch_points=None, max_ctas_per_sm=0):
         """``protocol`` / ``work_capacity`` / ``tsweep_groups``: launch details (``PROTOCOLS``; the
         work list of the fast-path protocol holds ``work_capacity`` deferred points, default 1/8 of
         the largest launch + 1024 -- ``max_launch_points`` bounds that launch, default the grid;
@@ -57,6 +57,7 @@ class DeviceProblem:
         d.hint_fast_path = 1 if plan.fast_path else 0
         d.protocol = PROTOCOLS[protocol]
         d.tsweep_groups = int(tsweep_groups)
+        d.max_ctas_per_sm = int(max_ctas_per_sm)
         d.prism_inv_n = plan.prism_inv_n
         # work list of the fast-path protocol: owned by this problem (freed with it), one in-flight
         # launch sequence at a time (launches on one stream are ordered)
@@ -224,12 +225,14 @@ class DeviceOutputs:
         return total
 
 
-def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None, select="all"):
+def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None, select="all", peers=()):
     """Launch the fused kernel for points ``[n_begin, n_end)`` into ``out`` (asynchronous).
 
     ``select``: "all" fills every buffer ``out`` holds; "mueller" only the Mueller matrix (and the
     Stokes vector); "power" only the power planes, "no-power" everything else (used to take the power bookkeeping from the stable recursion
-    while r_ij / t_ij keep transfer-matrix semantics)."""
+    while r_ij / t_ij keep transfer-matrix semantics).  ``peers``: fused all-gather -- per peer GPU the
+    four device addresses (pp, ps, sp, ss planes, element 0 of this range) in that GPU's result
+    buffer, mapped into this process; the kernel stores r_ij there too (``ho_outputs_t.peer_r``)."""
     n_end = problem.n_points if n_end is None else n_end
     if n_end - n_begin > out.n:
         raise ValueError("output buffers are smaller than the requested point range")
@@ -253,6 +256,12 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
         if out.t is not None and select not in ("power", "mueller"):
             o.t_pp, o.t_ps, o.t_sp, o.t_ss = (out.t[i].data_ptr() for i in range(4))
             o.t_mode, o.t_mode_stride = out.t_mode.data_ptr(), out.t_mode.shape[1]
+        if len(peers) > nat.HO_MAX_PEERS:
+            raise ValueError(f"at most {nat.HO_MAX_PEERS} peers")
+        o.n_peers = len(peers)
+        for p, quad in enumerate(peers):
+            for k in range(4):
+                o.peer_r[p][k] = int(quad[k])
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:
         o = nat.OutputsF32()

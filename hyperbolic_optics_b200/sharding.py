@@ -106,31 +106,87 @@ def exchange_chunk(rows, ranges, index, n_chunks, rank, group=None):
 
 
 class GatheredSweep:
-    """One sweep sharded over ``world_size`` GPUs, every rank ending with the WHOLE result.
+    """One sweep sharded over ``world_size`` GPUs, every rank ending with the WHOLE result
+    (``r`` ``[4, N]`` complex128 and ``mueller`` ``[N, 4, 4]`` in presentation order).
 
-    Rank ``r`` computes its slab in ``n_chunks`` launches directly into its place in the full-size
-    buffers (``r`` ``[4, N]`` complex128, ``mueller`` ``[N, 4, 4]``).  As soon as chunk ``c`` is
-    computed, a second stream exchanges its four ``r_ij`` planes with all peers (64 B per point over
-    NVLink) while chunk ``c + 1`` computes.  The Mueller planes (128 of the 192 B per point) are NOT
-    sent: they are a pure function of ``r_ij`` and HBM is 7x faster than an NVLink port, so each rank
-    rebuilds them for the chunks it received with one ``ho_polarimetry`` pass, also behind the next
-    exchange.  Step time ~ max(compute, exchange) + one chunk's tail, not their sum."""
+    ``transport="fused"`` (default when symmetric memory is available): the result buffers live in
+    symmetric memory (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into
+    every process over NVSwitch) and the reflection kernel itself performs the all-gather -- besides
+    its local planes it stores each r_ij into the peers' buffers (``ho_outputs_t.peer_r``), so the
+    NVLink transfer overlaps the arithmetic point by point inside ONE kernel, with no separate
+    communication kernels competing for SMs.  The step is bound by NVLink ingest
+    (64 B x the points of the other ranks per GPU at <= 900 GB/s), i.e. max(compute, exchange).
+    ``transport="dma"``: same symmetric buffers, but each computed chunk is PUSHED into the peers'
+    buffers by the copy engines (``cudaMemcpyAsync`` peer-to-peer, one stream per peer) while the
+    next chunk computes -- no SM takes part in the transfer, which leaves them free for the Mueller
+    rebuild of the chunks that have already arrived; the choice for NVLink-bound steps (N >= 4).
+    ``transport="p2p"``: chunks are exchanged by grouped ``ncclSend`` / ``ncclRecv`` on a second
+    stream behind the next chunk's compute (also what the gloo CPU test exercises).
 
-    def __init__(self, plan, backend, device, world_size, rank, n_chunks=8, mueller=True, group=None):
+    Either way the Mueller planes (128 of the 192 B per point) are NOT sent: they are a pure
+    function of r_ij and HBM is 7x faster than an NVLink port, so each rank rebuilds them for the
+    chunks it received with one ``ho_polarimetry`` pass on a side stream, behind the next chunk."""
+
+    def __init__(self, plan, backend, device, world_size, rank, n_chunks=None, mueller=True, group=None, transport="auto",
+                 ctas_per_sm=None):
         import torch
+        import torch.distributed as dist
 
         from . import engine
 
         self.plan, self.world, self.rank, self.group = plan, world_size, rank, group
         self.ranges = [point_range(plan, world_size, r) for r in range(world_size)]
-        self.n_chunks = max(1, int(n_chunks))
+        self.n_chunks = max(1, int(n_chunks if n_chunks else (8 if world_size >= 4 else 4)))
         longest = max(chunk_range(lo, hi, 0, self.n_chunks)[1] - lo for lo, hi in self.ranges)
-        self.problem = engine.DeviceProblem(plan, backend, device, max_launch_points=longest)
+        # (chunks may be shorter than the size at which the library picks the fast-path protocol by itself)
+        # From 4 GPUs on the fused step is NVLink-bound (64 B x 3/4 .. 7/8 of the sweep into every GPU),
+        # not compute-bound: the kernel then runs as one wave of 2 CTAs per SM so that part of every SM
+        # is free for the Mueller rebuild on the side stream (measured at N = 8: 11.1 ms at full
+        # residency, 11.3 with 1 CTA per SM -- too few stores in flight --, 10.4 with 2).
+        if ctas_per_sm is None:
+            ctas_per_sm = 2 if (world_size >= 4 and mueller) else 0
+        self.problem = engine.DeviceProblem(plan, backend, device, max_launch_points=longest,
+                                            protocol="fast" if plan.fast_path else "auto", max_ctas_per_sm=ctas_per_sm)
+        dev = self.problem.device
         n = plan.n_points
-        self.r = torch.empty((4, n), dtype=torch.complex128, device=self.problem.device)
-        self.mueller = torch.empty((n, 4, 4), dtype=torch.float64, device=self.problem.device) if mueller else None
-        self.comm = torch.cuda.Stream(self.problem.device)
+        self.n = n
+        self._hdl = None
+        self.transport_error = None
+        if transport == "auto":
+            # measured on B200 at N = 2 and 8 (profiles/README.md): the fused kernel beats both the
+            # copy-engine push and grouped ncclSend/ncclRecv
+            transport = "fused"
+            auto = True
+        else:
+            auto = False
+        if transport in ("fused", "dma"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                flat = symm.empty(4 * n * 2, dtype=torch.float64, device=dev)
+                self._hdl = symm.rendezvous(flat, group if group is not None else dist.group.WORLD)
+                self._flat = flat
+                self.r = torch.view_as_complex(flat.view(4, n, 2))
+                self._peer_base = [int(p) for p in self._hdl.buffer_ptrs]
+                self._peer_r = {r: torch.view_as_complex(self._hdl.get_buffer(r, (4, n, 2), torch.float64))
+                                for r in range(world_size) if r != rank}
+            except Exception as exc:  # noqa: BLE001 - no symmetric memory on this system: exchange by NCCL instead
+                if not auto:
+                    raise
+                self._hdl, self.transport_error = None, repr(exc)
+        self.transport = transport if self._hdl is not None else "p2p"
+        self._push = [torch.cuda.Stream(dev) for _ in range(world_size - 1)] if self.transport == "dma" else []
+        self._comm = torch.cuda.Stream(dev) if self.transport == "dma" else None
+        if self._hdl is None:
+            self.r = torch.empty((4, n), dtype=torch.complex128, device=dev)
+        self.mueller = torch.empty((n, 4, 4), dtype=torch.float64, device=dev) if mueller else None
+        self.side = torch.cuda.Stream(dev, priority=-1)
         self.bytes_received = 64 * (n - (self.ranges[rank][1] - self.ranges[rank][0]))
+
+    def _peers(self, lo):
+        """Device addresses of element ``lo`` of the four planes in every other rank's buffer."""
+        return [[base + 16 * (k * self.n + lo) for k in range(4)]
+                for r, base in enumerate(self._peer_base) if r != self.rank]
 
     def run(self, stream=None):
         """Enqueue one whole step (asynchronous); the caller synchronises."""
@@ -139,34 +195,50 @@ class GatheredSweep:
         from . import engine, polarimetry
 
         compute = stream or torch.cuda.current_stream(self.problem.device)
+        fused, dma = self.transport == "fused", self.transport == "dma"
         rows = [self.r[i] for i in range(4)]
-        arrived = []
+        if fused or dma:
+            # nobody may still be reading the previous step's planes when peers start overwriting them
+            with torch.cuda.stream(compute):
+                self._hdl.barrier(channel=0)
         for c in range(self.n_chunks):
             lo, hi = chunk_range(*self.ranges[self.rank], c, self.n_chunks)
             if hi > lo:
                 view = engine.DeviceOutputs.view(self.r[:, lo:hi], None if self.mueller is None else self.mueller[lo:hi])
-                engine.reflect(self.problem, view, lo, hi, stream=compute)
-            done = torch.cuda.Event()
-            done.record(compute)
-            self.comm.wait_event(done)
-            with torch.cuda.stream(self.comm):
-                for work in exchange_chunk(rows, self.ranges, c, self.n_chunks, self.rank, self.group):
-                    work.wait()
-                ev = torch.cuda.Event()
-                ev.record(self.comm)
-            arrived.append(ev)
-            if self.mueller is not None and c > 0:
-                self._rebuild_mueller(c - 1, arrived[c - 1], compute, polarimetry)
-        if self.mueller is not None:
-            self._rebuild_mueller(self.n_chunks - 1, arrived[-1], compute, polarimetry)
-        else:
-            compute.wait_event(arrived[-1])
-
-    def _rebuild_mueller(self, c, arrived, compute, polarimetry):
-        compute.wait_event(arrived)
-        for src in range(self.world):
-            if src == self.rank:
-                continue
-            lo, hi = chunk_range(*self.ranges[src], c, self.n_chunks)
-            if hi > lo:
-                polarimetry.mueller_into([self.r[i, lo:hi] for i in range(4)], self.mueller[lo:hi], stream=compute)
+                engine.reflect(self.problem, view, lo, hi, stream=compute, peers=self._peers(lo) if fused else ())
+            arrived = torch.cuda.Event()
+            if fused:
+                with torch.cuda.stream(compute):
+                    self._hdl.barrier(channel=1 + c % 7)     # every rank's chunk c has landed everywhere
+                arrived.record(compute)
+            elif dma:
+                done = torch.cuda.Event()
+                done.record(compute)
+                for st, (peer, view) in zip(self._push, self._peer_r.items()):
+                    st.wait_event(done)
+                    with torch.cuda.stream(st):
+                        for k in range(4):
+                            view[k, lo:hi].copy_(self.r[k, lo:hi], non_blocking=True)
+                    self._comm.wait_stream(st)
+                with torch.cuda.stream(self._comm):
+                    self._hdl.barrier(channel=1 + c % 7)     # every rank has pushed its chunk c
+                    arrived.record(self._comm)
+            else:
+                done = torch.cuda.Event()
+                done.record(compute)
+                self.side.wait_event(done)
+                with torch.cuda.stream(self.side):
+                    for work in exchange_chunk(rows, self.ranges, c, self.n_chunks, self.rank, self.group):
+                        work.wait()
+                arrived.record(self.side)
+            if self.mueller is not None:
+                self.side.wait_event(arrived)
+                for src in range(self.world):
+                    if src == self.rank:
+                        continue
+                    a, b = chunk_range(*self.ranges[src], c, self.n_chunks)
+                    if b > a:
+                        polarimetry.mueller_into([self.r[i, a:b] for i in range(4)], self.mueller[a:b], stream=self.side)
+            else:
+                compute.wait_event(arrived)
+        compute.wait_stream(self.side)

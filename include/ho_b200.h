@@ -27,8 +27,9 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 11
+#define HO_ABI_VERSION 12
 #define HO_MAX_LAYERS 24
+#define HO_MAX_PEERS 15
 
 typedef struct { double re, im; } ho_c128;
 
@@ -96,7 +97,10 @@ typedef struct {
   int32_t tsweep_groups;         /* thickness axis (T > 1): 0 = warp-cooperative kernel, groups per warp chosen by
                                     the library; 1..32 = that many (f,a,b) groups per warp; -1 = one thread per
                                     point, no reuse of the t-independent sub-stack */
-  int32_t reserved0;
+  int32_t max_ctas_per_sm;       /* 0: the library's launch shape.  k > 0: the point-per-thread kernels run as ONE wave of
+                                    k CTAs per SM (grid-stride), leaving the rest of every SM to kernels on other
+                                    streams -- used by the fused all-gather once the step is NVLink-bound, so that the
+                                    receivers' Mueller rebuild overlaps it */
   /* Work list of the fast-path protocol: caller-owned device scratch of work_capacity + 1 uint32
      (entry 0 = number of deferred points of the last launch, then their indices relative to
      n_begin).  Launches that share a list must be ordered (same stream).  NULL: the general
@@ -155,6 +159,16 @@ typedef struct {
      Fluxes are Hermitian forms in (a_p, a_s), so these four determine R, T, A_i of ANY Jones
      state (fields.py:102-118 accepts a complex (a_s, a_p) pair). */
   int32_t power_states;
+  /* Fused all-gather over NVLink (multi-GPU): besides the local r_pp .. r_ss planes the
+     kernel stores every reflection coefficient into n_peers further destinations -- pointers into
+     the result buffers of the other GPUs of the box, mapped into this process (peer memory over
+     NVSwitch: CUDA IPC / symmetric memory), each addressing element 0 of the launched range like
+     r_pp does.  The transfer then overlaps the arithmetic point by point inside ONE kernel; the
+     stores are visible to the owner after this stream's work has completed and the ranks have
+     synchronised.  0: none.  (Mueller planes are not mirrored: they are a pure function of r_ij and
+     HBM is 7x faster than an NVLink port -- the receiver rebuilds them with ho_polarimetry.) */
+  int32_t n_peers;
+  ho_c128* peer_r[HO_MAX_PEERS][4]; /* [peer][pp, ps, sp, ss] */
 } ho_outputs_t;
 
 /* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /
