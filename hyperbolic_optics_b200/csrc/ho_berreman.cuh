@@ -50,11 +50,11 @@ template <typename T> __device__ __forceinline__ Vec4<T> sel(bool c, const Vec4<
 template <typename T> __device__ __forceinline__ Sym6<T> rotate_z(const Sym6<T>& s, T cb, T sb) {
   T c2 = cb * cb, s2 = sb * sb, cs = cb * sb;
   Sym6<T> r;
-  r.xx = c2 * s.xx - (T(2) * cs) * s.xy + s2 * s.yy;
-  r.xy = cs * (s.xx - s.yy) + (c2 - s2) * s.xy;
-  r.xz = cb * s.xz - sb * s.yz;
-  r.yy = s2 * s.xx + (T(2) * cs) * s.xy + c2 * s.yy;
-  r.yz = sb * s.xz + cb * s.yz;
+  r.xx = fma(s2, s.yy, fnma(T(2) * cs, s.xy, c2 * s.xx));
+  r.xy = fma(c2 - s2, s.xy, cs * (s.xx - s.yy));
+  r.xz = fnma(sb, s.yz, cb * s.xz);
+  r.yy = fma(c2, s.yy, fma(T(2) * cs, s.xy, s2 * s.xx));
+  r.yz = fma(cb, s.yz, sb * s.xz);
   r.zz = s.zz;
   return r;
 }
@@ -67,11 +67,11 @@ template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k,
   Delta<T, true> D;
   D.a = -(k * (e.xz * ie));
   D.b = -(k * (e.yz * ie));
-  D.d = mu - k2 * ie;
+  D.d = fnma(k2, ie, mu);
   D.f = -mu;
-  D.g = e.yz * e.xz * ie - e.xy;
-  D.h = k2 * im - e.yy + e.yz * e.yz * ie;
-  D.j = e.xx - e.xz * e.xz * ie;
+  D.g = fma(e.yz * e.xz, ie, -e.xy);
+  D.h = fma(e.yz * e.yz, ie, fnma(T(1), e.yy, k2 * im));
+  D.j = fnma(e.xz * e.xz, ie, e.xx);
   D.c = mk<T>(T(0), T(0));
   D.e = mk<T>(T(0), T(0));
   return D;
@@ -98,17 +98,17 @@ template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T, t
   Vec4<T> r;
   r.v0 = fma(D.d, v.v3, fma(D.b, v.v1, D.a * v.v0));
   r.v1 = D.f * v.v2;
-  r.v2 = fma(D.h, v.v1, D.g * v.v0) - D.b * v.v3;
-  r.v3 = fma(D.a, v.v3, D.j * v.v0) - D.g * v.v1;
+  r.v2 = fnma(D.b, v.v3, fma(D.h, v.v1, D.g * v.v0));
+  r.v3 = fnma(D.g, v.v1, fma(D.a, v.v3, D.j * v.v0));
   return r;
 }
 
 template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T>& D, const Vec4<T>& v) {
   Vec4<T> r;
   r.v0 = fma(D.d, v.v3, fma(D.c, v.v2, fma(D.b, v.v1, D.a * v.v0)));
-  r.v1 = fma(D.f, v.v2, D.e * v.v1) - D.c * v.v3;
-  r.v2 = fma(D.e, v.v2, fma(D.h, v.v1, D.g * v.v0)) - D.b * v.v3;
-  r.v3 = fma(D.a, v.v3, D.j * v.v0) - D.g * v.v1;
+  r.v1 = fnma(D.c, v.v3, fma(D.f, v.v2, D.e * v.v1));
+  r.v2 = fnma(D.b, v.v3, fma(D.e, v.v2, fma(D.h, v.v1, D.g * v.v0)));
+  r.v3 = fnma(D.g, v.v1, fma(D.a, v.v3, D.j * v.v0));
   return r;
 }
 
@@ -116,9 +116,9 @@ template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T>& 
 template <typename T> __device__ __forceinline__ void charpoly(const Delta<T, true>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
   cx<T> a2 = D.a * D.a, ab = D.a * D.b;
   c3 = T(-2) * D.a;
-  c2 = a2 - D.d * D.j - D.f * D.h;
-  c1 = T(2) * (D.f * (D.a * D.h - D.b * D.g));
-  c0 = D.f * (T(2) * (ab * D.g) - a2 * D.h + D.b * D.b * D.j + D.d * (D.g * D.g + D.h * D.j));
+  c2 = fnma(D.f, D.h, fnma(D.d, D.j, a2));
+  c1 = T(2) * (D.f * fnma(D.b, D.g, D.a * D.h));
+  c0 = D.f * fma(D.d, fma(D.h, D.j, D.g * D.g), fma(D.b * D.b, D.j, fnma(a2, D.h, T(2) * (ab * D.g))));
 }
 
 template <typename T> __device__ __forceinline__ void charpoly(const Delta<T>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
@@ -137,7 +137,7 @@ template <typename T> __device__ __forceinline__ void charpoly(const Delta<T>& D
 // when the loss is tiny (seen in FP32 on SiC at 1700 cm^-1).
 template <typename T> __device__ __forceinline__ void quad_roots(cx<T> bq, cx<T> cq, cx<T>& y0, cx<T>& y1) {
   const T tau = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
-  cx<T> sq = csqrt(bq * bq - T(4) * cq);
+  cx<T> sq = csqrt(fma(bq, bq, T(-4) * cq));
   if (norm2(sq) <= tau * norm2(bq)) sq = mk<T>(T(0), T(0));
   bool plus = cmulc(bq, sq).re >= T(0);
   cx<T> t = T(-0.5) * (plus ? bq + sq : bq - sq);
@@ -244,7 +244,7 @@ template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c
 #pragma unroll 1
   for (int it = 0;; ++it) {
     b1 = c3 - u;
-    b0 = c2 - v - u * b1;
+    b0 = fnma(u, b1, c2 - v);
     cx<T> t1 = u * b0, t2 = v * b1, t3 = v * b0;
     cx<T> r1 = c1 - t1 - t2;
     cx<T> r0 = c0 - t3;
@@ -252,19 +252,19 @@ template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c
     if (it == max_steps) break;
     cx<T> umb = u - b1;
     cx<T> j22 = v - b0;
-    cx<T> j11 = j22 - u * umb;
+    cx<T> j11 = fnma(u, umb, j22);
     cx<T> j21 = -(v * umb);
-    cx<T> det = j11 * j22 - umb * j21;
+    cx<T> det = fnma(umb, j21, j11 * j22);
     if (!(norm2(det) > T(0))) break;
     cx<T> idet = recip(det);
-    cx<T> du = (r0 * umb - r1 * j22) * idet;
-    cx<T> dv = (r1 * j21 - r0 * j11) * idet;
+    cx<T> du = fnma(r1, j22, r0 * umb) * idet;
+    cx<T> dv = fnma(r0, j11, r1 * j21) * idet;
     u = u + du;
     v = v + dv;
     if (norm2(du) + norm2(dv) <= step_tol2 * (norm2(u) + norm2(v))) {
       converged = true;
       b1 = c3 - u;
-      b0 = c2 - v - u * b1;
+      b0 = fnma(u, b1, c2 - v);
       break;
     }
   }
@@ -333,9 +333,9 @@ template <typename T, bool FAST = false> __device__ __forceinline__ Spectrum<T> 
 // h(x) = h0 + h1 x with h q_b = 1 (mod q_f): the forward spectral projector is q_b(D) h(D)
 template <typename T> __device__ __forceinline__ void projector_coeffs(const Spectrum<T>& s, cx<T>& h0, cx<T>& h1) {
   cx<T> U = s.sf - s.sb, V = s.pb - s.pf;
-  cx<T> R = U * U * s.pf + U * V * s.sf + V * V;
+  cx<T> R = fma(V, V, fma(U * V, s.sf, (U * U) * s.pf));
   cx<T> iR = recip(R);
-  h0 = (U * s.sf + V) * iR;
+  h0 = fma(U, s.sf, V) * iR;
   h1 = -(U * iR);
 }
 
@@ -353,7 +353,7 @@ template <typename T, bool NM> __device__ __forceinline__ Vec4<T> project_forwar
 // growth = max |Re(c lambda)| of the two modes
 template <typename T> __device__ __forceinline__ void pair_modes(cx<T> s, cx<T> p, cx<T> c, cx<T>& lam_s, cx<T>& phi_s, cx<T>& dd, bool& separated, T& growth) {
   cx<T> m = T(0.5) * s;
-  cx<T> h = csqrt(m * m - p);
+  cx<T> h = csqrt(fma(m, m, -p));
   if ((c * h).re < T(0)) h = -h;
   lam_s = m - h;
   cx<T> lam_g = m + h;
@@ -406,15 +406,15 @@ template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> lam_
 // alpha(x) = (phi_s - dd lam_s) + dd x the linear interpolant of exp(c x) on each root pair
 template <typename T> __device__ __forceinline__ void cubic_coeffs(const Spectrum<T>& s, cx<T> h0, cx<T> h1, cx<T> lf, cx<T> phf, cx<T> ddf,
                                                                   cx<T> lb, cx<T> phb, cx<T> ddb, cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
-  cx<T> ab0 = phb - ddb * lb;
-  cx<T> d0 = (phf - ddf * lf) - ab0, d1 = ddf - ddb;
+  cx<T> ab0 = fnma(ddb, lb, phb);
+  cx<T> d0 = fnma(ddf, lf, phf) - ab0, d1 = ddf - ddb;
   cx<T> g0 = d0 * h0, g1 = fma(d1, h0, d0 * h1), g2 = d1 * h1;
   // q_f q_b = x^4 + c3 x^3 + c2 x^2 + c1 x + c0
   cx<T> c3 = -(s.sf + s.sb), c2 = fma(s.sf, s.sb, s.pf + s.pb), c1 = -fma(s.sf, s.pb, s.sb * s.pf), c0 = s.pf * s.pb;
-  a3 = g1 - g2 * (s.sb + c3);
-  a2 = fma(g2, s.pb - c2, g0 - s.sb * g1);
-  a1 = fma(s.pb, g1, ddb - s.sb * g0) - g2 * c1;
-  a0 = fma(s.pb, g0, ab0) - g2 * c0;
+  a3 = fnma(g2, s.sb + c3, g1);
+  a2 = fma(g2, s.pb - c2, fnma(s.sb, g1, g0));
+  a1 = fnma(g2, c1, fma(s.pb, g1, fnma(s.sb, g0, ddb)));
+  a0 = fnma(g2, c0, fma(s.pb, g0, ab0));
 }
 
 // Thin-film switch of both recursions: all four |Re(c lambda)| below this.  The cubic mixes the four
@@ -538,9 +538,9 @@ template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs
 #pragma unroll 1
   for (int it = 0; it < 3 && !done; ++it) {
     b1 = c3 - u;
-    b0 = c2 - v - u * b1;
-    du = (c1 - u * b0 - v * b1) * idy;
-    dv = (c0 - v * b0) * idy;
+    b0 = fnma(u, b1, c2 - v);
+    du = fnma(v, b1, fnma(u, b0, c1)) * idy;
+    dv = fnma(v, b0, c0) * idy;
     u = u + du;
     v = v + dv;
     T nv = norm2(v), ndu = norm2(du);
@@ -548,19 +548,19 @@ template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs
   }
   if (!done) return false;
   b1 = c3 - u;
-  b0 = c2 - v - u * b1;
+  b0 = fnma(u, b1, c2 - v);
   Spectrum<T> s;
   s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   // pair 0
   cx<T> d0 = T(0.5) * s.sf, d1 = T(0.5) * s.sb;
-  cx<T> z0 = c * csqrt(d0 * d0 - s.pf), z1 = c * csqrt(d1 * d1 - s.pb);
+  cx<T> z0 = c * csqrt(fma(d0, d0, -s.pf)), z1 = c * csqrt(fma(d1, d1, -s.pb));
   cx<T> x0 = c * d0, x1 = c * d1;
   if (!(thin_film(ho_abs(z0.re), ho_abs(z1.re)) && norm2(x0) < T(1e-10) && norm2(x1) < T(1e-10))) return false;
   cx<T> A0, S0, A1, S1;
   cosh_sinhc(z0, A0, S0);
   cosh_sinhc(z1, A1, S1);
   const cx<T> one = mk<T>(T(1), T(0));
-  cx<T> e0 = one + x0 + T(0.5) * (x0 * x0), e1 = one + x1 + T(0.5) * (x1 * x1);  // e^{c delta}, |c delta| < 1e-5
+  cx<T> e0 = fma(T(0.5) * x0, x0, one + x0), e1 = fma(T(0.5) * x1, x1, one + x1);  // e^{c delta}, |c delta| < 1e-5
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   cubic_coeffs(s, h0, h1, d0, e0 * A0, e0 * (c * S0), d1, e1 * A1, e1 * (c * S1), a0, a1, a2, a3);
@@ -569,7 +569,7 @@ template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs
 
 // 2x2 inverse of [[m00, m01], [m10, m11]]
 template <typename T> __device__ __forceinline__ void inv2(cx<T> m00, cx<T> m01, cx<T> m10, cx<T> m11, cx<T>& n00, cx<T>& n01, cx<T>& n10, cx<T>& n11) {
-  cx<T> idet = recip(m00 * m11 - m01 * m10);
+  cx<T> idet = recip(fnma(m01, m10, m00 * m11));
   n00 = m11 * idet; n01 = -(m01 * idet); n10 = -(m10 * idet); n11 = m00 * idet;
 }
 
@@ -671,7 +671,7 @@ template <typename T> __device__ __forceinline__ Vec4<T> iso_matvec(cx<T> d, cx<
 
 template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, cx<T> mu, cx<T> c, bool stable, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   T k2 = k * k;
-  cx<T> d = mu - k2 * recip(eps), f = -mu, h = k2 * recip(mu) - eps, j = eps;
+  cx<T> d = fnma(k2, recip(eps), mu), f = -mu, h = fma(k2, recip(mu), -eps), j = eps;
   cx<T> kz2 = eps * mu - k2;
   Vec4<T> dy0 = iso_matvec(d, f, h, j, y0), dy1 = iso_matvec(d, f, h, j, y1);
   if (!stable) {
@@ -719,7 +719,7 @@ template <typename T> __device__ __forceinline__ void iso_crystal_exit_plane(T k
   T k2 = k * k;
   cx<T> kz = forward_sqrt(eps * mu - k2);
   y0.v0 = zero; y0.v1 = -mu; y0.v2 = kz; y0.v3 = zero;
-  y1.v0 = mu - k2 * recip(eps); y1.v1 = zero; y1.v2 = zero; y1.v3 = kz;
+  y1.v0 = fnma(k2, recip(eps), mu); y1.v1 = zero; y1.v2 = zero; y1.v3 = kz;
 }
 
 // columns 0 and 2 of the isotropic exit matrix (reference layers.py:190-238)
@@ -732,15 +732,16 @@ template <typename T> __device__ __forceinline__ void exit_iso_plane(cx<T> cf, T
 // prism rows + 2x2 minors (reference layers.py:109-152, structure.py:285-304); the common 1/2 cancels
 template <typename T> __device__ __forceinline__ void reflect_from_plane(const Vec4<T>& y0, const Vec4<T>& y1, T inv_c, T inv_nc, T inv_n,
                                                                         cx<T>& r_pp, cx<T>& r_ps, cx<T>& r_sp, cx<T>& r_ss) {
-  cx<T> g00 = y0.v1 - inv_nc * y0.v2, g10 = y0.v1 + inv_nc * y0.v2;
-  cx<T> g20 = inv_c * y0.v0 + inv_n * y0.v3, g30 = inv_n * y0.v3 - inv_c * y0.v0;
-  cx<T> g02 = y1.v1 - inv_nc * y1.v2, g12 = y1.v1 + inv_nc * y1.v2;
-  cx<T> g22 = inv_c * y1.v0 + inv_n * y1.v3, g32 = inv_n * y1.v3 - inv_c * y1.v0;
-  cx<T> ib = recip(g00 * g22 - g02 * g20);
-  r_pp = (g00 * g32 - g30 * g02) * ib;
-  r_ps = (g00 * g12 - g10 * g02) * ib;
-  r_sp = (g30 * g22 - g32 * g20) * ib;
-  r_ss = (g10 * g22 - g12 * g20) * ib;
+  cx<T> g00 = fnma(inv_nc, y0.v2, y0.v1), g10 = fma(inv_nc, y0.v2, y0.v1);
+  cx<T> n0 = inv_n * y0.v3, n1 = inv_n * y1.v3;
+  cx<T> g20 = fma(inv_c, y0.v0, n0), g30 = fnma(inv_c, y0.v0, n0);
+  cx<T> g02 = fnma(inv_nc, y1.v2, y1.v1), g12 = fma(inv_nc, y1.v2, y1.v1);
+  cx<T> g22 = fma(inv_c, y1.v0, n1), g32 = fnma(inv_c, y1.v0, n1);
+  cx<T> ib = recip(fnma(g02, g20, g00 * g22));
+  r_pp = fnma(g30, g02, g00 * g32) * ib;
+  r_ps = fnma(g10, g02, g00 * g12) * ib;
+  r_sp = fnma(g32, g20, g30 * g22) * ib;
+  r_ss = fnma(g12, g20, g10 * g22) * ib;
 }
 
 // ---- power bookkeeping (reference fields.py:45-51, 120-282) ----

@@ -303,7 +303,11 @@ enum { MODE_ALL = 0, MODE_FIXUP = 1 };
 // FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only the deferred points.
 // work[0] = number of deferred points, work[1 .. cap] = their indices relative to n_begin.
 template <typename T, bool STABLE, bool NM, bool POWER, bool FAST>
+#ifdef HO_FAST_REGS   // experiment: cap the registers directly (resident CTAs follow from the register file)
+__global__ void __launch_bounds__(kThreads) __maxnreg__(FAST ? HO_FAST_REGS : HO_GEN_REGS)
+#else
 __global__ void __launch_bounds__(kThreads, FAST ? HO_FAST_BLOCKS : HO_MIN_BLOCKS)
+#endif
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
                unsigned* work, unsigned cap) {
   using namespace ho;

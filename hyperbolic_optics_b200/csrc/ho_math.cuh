@@ -27,6 +27,14 @@ template <typename T> __device__ __forceinline__ T norm2(cx<T> a) { return a.re 
 template <typename T> __device__ __forceinline__ cx<T> fma(cx<T> b, cx<T> c, cx<T> a) {
   return mk<T>(a.re + b.re * c.re - b.im * c.im, a.im + b.re * c.im + b.im * c.re);
 }
+// a - b*c  (four FMAs: the negations are operand modifiers; `a - b * c` would be a product plus a
+// subtraction, six instructions, because the compiler may not re-associate)
+template <typename T> __device__ __forceinline__ cx<T> fnma(cx<T> b, cx<T> c, cx<T> a) {
+  return mk<T>(a.re - b.re * c.re + b.im * c.im, a.im - b.re * c.im - b.im * c.re);
+}
+// a + s*c and a - s*c with a real s (two FMAs)
+template <typename T> __device__ __forceinline__ cx<T> fma(T s, cx<T> c, cx<T> a) { return mk<T>(a.re + s * c.re, a.im + s * c.im); }
+template <typename T> __device__ __forceinline__ cx<T> fnma(T s, cx<T> c, cx<T> a) { return mk<T>(a.re - s * c.re, a.im - s * c.im); }
 // conj(a)*b
 template <typename T> __device__ __forceinline__ cx<T> cmulc(cx<T> a, cx<T> b) {
   return mk<T>(a.re * b.re + a.im * b.im, a.re * b.im - a.im * b.re);

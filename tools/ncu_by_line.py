@@ -1,47 +1,55 @@
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump by source line."""
+"""Aggregate an `ncu -i <rep> --page source --csv --print-source cuda,sass` dump by CUDA source line:
+share of warp instructions, of FP64 instructions (DFMA/DMUL/DADD) and of stall samples per line.
+
+    python tools/ncu_by_line.py gpurun_out/<name>_srcsass.csv [top]
+"""
 import collections
 import csv
 import sys
 
 
 def main(path, top=45):
-    rows = list(csv.reader(open(path)))
-    cur_file, hdr = None, None
-    per_line = collections.defaultdict(lambda: [0, 0])
-    stall_tot = collections.Counter()
-    for r in rows:
+    cur_file, hdr, ix = None, None, None
+    per_line = collections.defaultdict(lambda: [0, 0, 0])
+    launch = 0
+    for r in csv.reader(open(path)):
         if not r:
+            continue
+        if r[0] == "Kernel Name":
+            launch += 1
             continue
         if r[0] == "File Path":
             cur_file = r[1].split("/")[-1]
             continue
+        if r[0] == "Function Name":
+            continue
         if r[0] == "Line No":
             hdr = r
+            ix = {h: i for i, h in enumerate(hdr)}
             continue
-        if r[0] == "Function Name" or hdr is None:
+        if hdr is None or launch > 1:   # first captured launch only
             continue
-        if r[0] not in ("", "-"):
-            d = dict(zip(hdr, r))
-            try:
-                line = int(r[0])
-            except ValueError:
-                continue
-            num = lambda x: int(x) if x not in ("", "-", None) else 0
-            inst = num(d["Instructions Executed"])
-            samp = num(d["# Samples"])
-            key = (cur_file, line, r[1].strip()[:100])
-            per_line[key][0] += inst
-            per_line[key][1] += samp
-            for k, v in d.items():
-                if k.startswith("stall_") and "Not Issued" not in k and v not in ("", "0", "-"):
-                    stall_tot[k] += int(v)
-    tot_inst = sum(v[0] for v in per_line.values())
-    tot_s = sum(v[1] for v in per_line.values())
-    print("total warp instructions", tot_inst, "samples", tot_s)
-    s = sum(stall_tot.values())
-    print("stall reasons (% of samples):", [(k, round(100 * v / s, 1)) for k, v in stall_tot.most_common(8)])
+        try:
+            line = int(r[0])
+        except ValueError:
+            continue
+        num = lambda x: int(x) if x not in ("", "-") else 0
+        inst, samp = num(r[ix["Instructions Executed"]]), num(r[ix["# Samples"]])
+        key = (cur_file, line, r[1].strip()[:90])
+        per_line[key][0] += inst
+        per_line[key][1] += samp
+        toks = r[3].split()
+        if toks:
+            op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
+            if op.startswith(("DFMA", "DMUL", "DADD")):
+                per_line[key][2] += inst
+    tot = sum(v[0] for v in per_line.values())
+    tots = sum(v[1] for v in per_line.values())
+    totf = sum(v[2] for v in per_line.values())
+    print(f"{path}: warp instructions {tot}, FP64 {totf} ({100 * totf / max(tot, 1):.1f} %), samples {tots}")
     for key, v in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
-        print(f"{100 * v[0] / tot_inst:5.1f}% inst {100 * v[1] / tot_s:5.1f}% samp  {key[0]}:{key[1]}  {key[2]}")
+        print(f"{100 * v[0] / tot:5.1f}% inst {100 * v[2] / max(totf, 1):5.1f}% fp64 {100 * v[1] / max(tots, 1):5.1f}% samp  "
+              f"{key[0]}:{key[1]}  {key[2]}")
 
 
 if __name__ == "__main__":

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--points", type=int, default=100761600)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--json", default="")
+    ap.add_argument("--only", default="", help="substring of the request names to run")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     n = args.points
@@ -65,6 +66,8 @@ def main():
     peak, src = hbm_peak()
     rows = []
     for name, (want, mueller, mats, wbytes) in REQUESTS.items():
+        if args.only and args.only.lower() not in name.lower():
+            continue
         for _ in range(3):
             out = pol.run(P, want, mueller=mueller, decomposition_matrices=mats)
             del out
