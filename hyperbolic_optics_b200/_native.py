@@ -12,11 +12,12 @@ from pathlib import Path
 
 HO_MAX_LAYERS = 24
 HO_MAX_PEERS = 15
-HO_ABI_VERSION = 12
+HO_ABI_VERSION = 13
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
 HO_PROTOCOL_AUTO, HO_PROTOCOL_SINGLE, HO_PROTOCOL_FAST_FIXUP = 0, 1, 2
+HO_HINT_NONE, HO_HINT_UNTILTED, HO_HINT_TILTED_THIN = 0, 1, 2
 
 
 class c128(C.Structure):

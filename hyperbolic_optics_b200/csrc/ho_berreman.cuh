@@ -283,14 +283,15 @@ template <typename T> __device__ __forceinline__ cx<T> forward_sqrt(cx<T> y) {
 // tensors up to the reference's hidden 1e-8 angle offsets -- every un-tilted crystal) the quartic
 // is a perturbed biquadratic and the forward pair comes from three square roots; otherwise
 // Ferrari + classification.  A biquadratic start that fails to converge falls back to Ferrari.
-// FAST (fast-path kernel): only the biquadratic start is compiled; a point that would need
-// Ferrari sets `bail` and is finished later by the general kernel.
-template <typename T, bool FAST = false> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail) {
+// FAST == 1 (fast-path kernel): only the biquadratic start is compiled; a point that would need
+// Ferrari sets `bail` and is finished later by the general kernel.  FAST == 2 (lean kernel for
+// tilted stacks): the general start values, as FAST == 0.
+template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail) {
   const T tau4 = T(1e-20);
   T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
   bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
   cx<T> u, v, b1, b0;
-  if constexpr (FAST) {
+  if constexpr (FAST == 1) {
     cx<T> y0, y1;
     quad_roots(c2, c0, y0, y1);
     cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
@@ -443,7 +444,7 @@ template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const
 // no projected intermediates.  Mixing all four exponentials in one polynomial costs log10 of their
 // ratio in digits (<= 2.6 here); thick films -- where that form loses the sub-dominant growing
 // mode, SURVEY 7.0-6a -- keep the invariant-subspace block form.
-template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+template <typename T, bool NM, int FAST = 0> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   cx<T> lf, phf, ddf, lb, phb, ddb;
@@ -459,7 +460,7 @@ template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ voi
     cubic_apply(D, a0, a1, a2, a3, y1);
     return;
   }
-  if constexpr (FAST) { bail = true; return; }  // thick film: left to the general kernel
+  if constexpr (FAST != 0) { bail = true; return; }  // thick film: left to the general kernel
   Vec4<T> dy0, dy1;
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy0);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy1);
@@ -582,7 +583,7 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 // Renormalises so that rows (Ex, Ey) of the forward part are the identity.
 // w[0..3] = (w00, w01, w10, w11): the 2x2 map W with Y_new = exp(cD) Y_old W, i.e. coordinates at
 // the top of the film -> coordinates at its bottom (used by the power bookkeeping only).
-template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+template <typename T, bool NM, int FAST = 0> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   // Thin film (all four |Re(c lambda)| < 3): nothing can overflow and the four exponentials are
@@ -606,7 +607,7 @@ template <typename T, bool NM, bool FAST = false> __device__ __forceinline__ voi
     y0 = t0;
     return;
   }
-  if constexpr (FAST) { bail = true; return; }  // thick film: left to the general kernel
+  if constexpr (FAST != 0) { bail = true; return; }  // thick film: left to the general kernel
   Vec4<T> dy;
   Vec4<T> zf0 = project_forward(D, s, h0, h1, y0, dy);
   Vec4<T> zf1 = project_forward(D, s, h0, h1, y1, dy);

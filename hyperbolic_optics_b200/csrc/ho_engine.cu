@@ -104,10 +104,12 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 // One layer applied to the running plane (right-to-left sweep).  w: coordinate map of a film in
 // the stable recursion (power bookkeeping only; dead code otherwise).
 // binv (EXTRAS): kernel exit basis -> the reference's exit-mode amplitudes (transmission coefficients).
-// FAST: fast-path build of the layer code (biquadratic start for exits, pair-symmetric closed form
-// for films, closed-form isotropic layers; no Ferrari, no block film); sets `bail`
-// when the point needs the general paths.
-template <typename T, bool STABLE, bool NM, bool EXTRAS, bool FAST = false>
+// FAST == 1: fast-path build of the layer code for un-tilted plans (biquadratic start for exits,
+// pair-symmetric closed form for films, closed-form isotropic layers; no Ferrari, no block film);
+// FAST == 2: lean build for tilted plans (general start values, thin films as one cubic in Delta; no
+// pair-symmetric form, no block / thick-film code).  Both set `bail` when the point needs the
+// general build (FAST == 0), which compiles everything.
+template <typename T, bool STABLE, bool NM, bool EXTRAS, int FAST = 0>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
                                             ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4],
                                             bool& bail, bool untilted = true) {
@@ -138,13 +140,13 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
     cx<T> c3, c2, c1, c0;
     charpoly(D, c3, c2, c1, c0);
-    if (L.kind == HO_ANISO_FILM && (FAST || untilted)) {
+    if (L.kind == HO_ANISO_FILM && (FAST == 1 || (FAST == 0 && untilted))) {
       // un-tilted thin crystal film: pair-symmetric closed form, no spectral split
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       bool general = false;
       film_pair_symmetric<T, NM, STABLE>(D, c3, c2, c1, c0, mk<T>(T(0), -(k0 * d)), y0, y1, w, general);
       if (!general) return;
-      if constexpr (FAST) { bail = true; return; }
+      if constexpr (FAST == 1) { bail = true; return; }
     }
     Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail);
     if (L.kind == HO_ANISO_EXIT) {
@@ -302,12 +304,8 @@ enum { MODE_ALL = 0, MODE_FIXUP = 1 };
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
 // FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only the deferred points.
 // work[0] = number of deferred points, work[1 .. cap] = their indices relative to n_begin.
-template <typename T, bool STABLE, bool NM, bool POWER, bool FAST>
-#ifdef HO_FAST_REGS   // experiment: cap the registers directly (resident CTAs follow from the register file)
-__global__ void __launch_bounds__(kThreads) __maxnreg__(FAST ? HO_FAST_REGS : HO_GEN_REGS)
-#else
+template <typename T, bool STABLE, bool NM, bool POWER, int FAST>
 __global__ void __launch_bounds__(kThreads, FAST ? HO_FAST_BLOCKS : HO_MIN_BLOCKS)
-#endif
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
                unsigned* work, unsigned cap) {
   using namespace ho;
@@ -354,8 +352,8 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
       cx<T> w[4];
-      apply_layer<T, STABLE, NM, POWER, FAST>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path != 0 && mode != MODE_FIXUP);
-      if constexpr (FAST) {
+      apply_layer<T, STABLE, NM, POWER, FAST>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path == HO_HINT_UNTILTED && mode != MODE_FIXUP);
+      if constexpr (FAST != 0) {
         if (bail) break;
       }
       if constexpr (POWER) {
@@ -363,7 +361,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
         wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];
       }
     }
-    if constexpr (FAST) {
+    if constexpr (FAST != 0) {
       if (bail) {  // left to the fix-up launch
         const double nan_mark = __longlong_as_double((long long)kSentinelBits);
         st_stream(out.r_pp + rel, mk<T>(T(nan_mark), T(nan_mark)));
@@ -450,7 +448,7 @@ tsweep_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<double> out, int64
         for (int l = l_hi; l >= l_lo; --l) {
           cx<T> w[4];
           bool bail = false;  // (general build: never set)
-          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path != 0);
+          apply_layer<T, STABLE, NM, POWER>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path == HO_HINT_UNTILTED);
           if constexpr (POWER) {
             flux_form(y0, y1, hf[l]);
             wm[l][0] = w[0]; wm[l][1] = w[1]; wm[l][2] = w[2]; wm[l][3] = w[3];
@@ -660,7 +658,7 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
     if (p->T > 1 && swept >= 0 && p->tsweep_groups >= 0)
       return launch_tsweep<STABLE, NM, POWER>(p, out, n_begin, n_end, swept, stream);
   }
-  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, false>;
+  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, 0>;
   const int grid = grid_for(n_end - n_begin, kern, p->max_ctas_per_sm);
   if constexpr (sizeof(T) == 8 && !POWER) {
     // (below ~4M points the second launch costs more than the leaner kernel saves)
@@ -668,18 +666,23 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
     const bool want = p->protocol == HO_PROTOCOL_FAST_FIXUP ||
                       (p->protocol == HO_PROTOCOL_AUTO && p->hint_fast_path != 0 && n >= (int64_t)1 << 22);
     if (want && p->work && p->work_capacity >= 0 && out.r_pp && n < ((int64_t)1 << 32)) {
-      const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, true>;
       // a list shorter than the deferred set makes the fix-up pass scan r_pp for the sentinel
       const int64_t cap = p->work_capacity < (int64_t)0x7fffffff ? p->work_capacity : (int64_t)0x7fffffff;
       if (cudaMemsetAsync(p->work, 0, sizeof(unsigned), stream) != cudaSuccess)
         return fail(HO_ERR_CUDA, "work list reset failed: %s", cudaGetErrorString(cudaGetLastError()));
-      reflect_kernel<T, STABLE, NM, false, true><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
-      reflect_kernel<T, STABLE, NM, false, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, p->work, (unsigned)cap);
+      if (p->hint_fast_path == HO_HINT_TILTED_THIN) {   // lean build: general start values, thin films only
+        const void* lean = (const void*)reflect_kernel<T, STABLE, NM, false, 2>;
+        reflect_kernel<T, STABLE, NM, false, 2><<<grid_for(n, lean, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
+      } else {                                          // fast build: un-tilted crystals
+        const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, 1>;
+        reflect_kernel<T, STABLE, NM, false, 1><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
+      }
+      reflect_kernel<T, STABLE, NM, false, 0><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, p->work, (unsigned)cap);
       g_launches.fetch_add(1);
       return 0;
     }
   }
-  reflect_kernel<T, STABLE, NM, POWER, false><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr, 0u);
+  reflect_kernel<T, STABLE, NM, POWER, 0><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr, 0u);
   return 0;
 }
 

@@ -54,7 +54,7 @@ class DeviceProblem:
         d.A, d.B, d.F, d.T = plan.A, plan.B, plan.F, plan.T
         d.n_layers = len(plan.layers)
         d.backend = BACKENDS[backend]
-        d.hint_fast_path = 1 if plan.fast_path else 0
+        d.hint_fast_path = int(plan.kernel_hint)
         d.protocol = PROTOCOLS[protocol]
         d.tsweep_groups = int(tsweep_groups)
         d.max_ctas_per_sm = int(max_ctas_per_sm)
@@ -63,7 +63,7 @@ class DeviceProblem:
         # launch sequence at a time (launches on one stream are ordered)
         self.work = None
         launch_points = min(plan.n_points, int(max_launch_points or plan.n_points))
-        wanted = protocol == "fast" or (protocol == "auto" and plan.fast_path and launch_points >= FAST_PATH_MIN_POINTS)
+        wanted = protocol == "fast" or (protocol == "auto" and plan.kernel_hint != 0 and launch_points >= FAST_PATH_MIN_POINTS)
         if wanted:
             cap = int(work_capacity) if work_capacity is not None else launch_points // 8 + 1024
             cap = max(0, min(cap, 0x7FFFFFFF))

@@ -79,6 +79,7 @@ class StackPlan:
     eps_prism: float | None = None
     k0_all: np.ndarray | None = None   # 2 pi f for every requested frequency (k0 may be collapsed to one entry)
     fast_path: bool = False            # every crystal un-tilted: the fast-path kernel applies (performance hint)
+    kernel_hint: int = 0               # ho_kernel_hint: 1 = un-tilted (fast build), 2 = tilted, thin films (lean build)
 
     @property
     def n_points(self):
@@ -240,8 +241,19 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
     if not plan.layers or plan.layers[-1].kind not in (KIND_ANISO_EXIT, KIND_ISO_EXIT):
         raise ValueError("the stack must end with a semi-infinite exit layer")
     _collapse_unswept_axes(plan)
+    crystals = [lp for lp in plan.layers if lp.kind in (KIND_ANISO_FILM, KIND_ANISO_EXIT) and not (lp.eps_scalar and lp.mu_scalar)]
     plan.fast_path = all(_untilted(lp) for lp in plan.layers if lp.kind in (KIND_ANISO_FILM, KIND_ANISO_EXIT))
+    if plan.fast_path:
+        plan.kernel_hint = 1
+    elif crystals and all(_optically_thin(lp, plan.k0_all) for lp in crystals if lp.kind == KIND_ANISO_FILM):
+        plan.kernel_hint = 2
     return plan
+
+
+def _optically_thin(lp, k0) -> bool:
+    """k0 d <= 0.5 for every sample: the mode exponentials of such a film stay within e^6 of each
+    other except next to a resonance, so the lean kernel's one-cubic film applies to most points."""
+    return float(np.max(k0)) * float(np.max(lp.thickness)) <= 0.5
 
 
 def _untilted(lp) -> bool:

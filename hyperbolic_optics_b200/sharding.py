@@ -146,7 +146,7 @@ class GatheredSweep:
         if ctas_per_sm is None:
             ctas_per_sm = 2 if (world_size >= 4 and mueller) else 0
         self.problem = engine.DeviceProblem(plan, backend, device, max_launch_points=longest,
-                                            protocol="fast" if plan.fast_path else "auto", max_ctas_per_sm=ctas_per_sm)
+                                            protocol="fast" if plan.kernel_hint else "auto", max_ctas_per_sm=ctas_per_sm)
         dev = self.problem.device
         n = plan.n_points
         self.n = n

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 12
+#define HO_ABI_VERSION 13
 #define HO_MAX_LAYERS 24
 #define HO_MAX_PEERS 15
 
@@ -77,6 +77,8 @@ typedef struct {
   double exit_n;           /* HO_ISO_EXIT: sqrt(eps_exit) */
 } ho_layer_t;
 
+enum ho_kernel_hint { HO_HINT_NONE = 0, HO_HINT_UNTILTED = 1, HO_HINT_TILTED_THIN = 2 };
+
 /* How ho_reflect launches the point-per-thread kernels (a launch detail: results are the same) */
 enum ho_protocol {
   HO_PROTOCOL_AUTO = 0,      /* fast-path kernel + fix-up launch when hint_fast_path is set, a work list is
@@ -89,10 +91,12 @@ typedef struct {
   int32_t A, B, F, T;            /* canonical batch sizes (axes.py:21) */
   int32_t n_layers;              /* layers below the prism, <= HO_MAX_LAYERS */
   int32_t backend;               /* ho_backend */
-  int32_t hint_fast_path;        /* 1: every crystal layer is un-tilted (z is a principal axis of its rotated
-                                    tensors up to the reference's 1e-8 offsets), so the fast-path kernel applies
-                                    to (almost) every point; a performance hint only -- points it cannot
-                                    evaluate are finished by the general kernel either way */
+  int32_t hint_fast_path;        /* ho_kernel_hint.  HO_HINT_UNTILTED: every crystal layer is un-tilted (z is a principal
+                                    axis of its rotated tensors up to the reference's 1e-8 offsets): the fast-path
+                                    kernel applies to (almost) every point.  HO_HINT_TILTED_THIN: tilted crystals whose
+                                    films are optically thin: the lean kernel (general start values, films as one
+                                    cubic in Delta) applies.  A performance hint only -- points the chosen kernel
+                                    cannot evaluate are finished by the general kernel either way */
   int32_t protocol;              /* ho_protocol */
   int32_t tsweep_groups;         /* thickness axis (T > 1): 0 = warp-cooperative kernel, groups per warp chosen by
                                     the library; 1..32 = that many (f,a,b) groups per warp; -1 = one thread per

@@ -152,10 +152,13 @@ def test_full_size_baseline_configs_vs_oracle(name, built_library):
             # the protocol the bench times: fast-path kernel + fix-up launch over the work list
             # (non-empty on C4: near-normal incidence and ENZ frequencies of the hBN film; the
             # fast-path kernel evaluates every point of C1 itself)
-            assert s.plan.fast_path and n >= engine.FAST_PATH_MIN_POINTS
+            assert s.plan.fast_path and s.plan.kernel_hint == 1 and n >= engine.FAST_PATH_MIN_POINTS
             assert deferred is not None and (0 if name == "c1" else 1) <= deferred < cap, (deferred, cap)
+        elif name == "c4_tilted":
+            # tilted axes, optically thin film: lean kernel (general start values, one-cubic film) + fix-up
+            assert s.plan.kernel_hint == 2 and deferred is not None and 0 <= deferred < cap, (deferred, cap)
         else:
-            assert deferred is None     # tilted plans / small grids / thickness sweeps: general kernels
+            assert deferred is None     # small grids / thickness sweeps: the general kernels alone
         # C5's transfer product is noise by design (BASELINE names the scattering backend for it)
         points, worst = _check(s, payload, backend=backend, min_trusted=0.5 if name == "c5" else 0.9, arbitrate=name == "c5")
         print(f"{name}/{backend}: {n} points, deferred {deferred}, sub-lattice {points} points, worst e_J {worst:.2e}")

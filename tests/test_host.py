@@ -259,6 +259,10 @@ def test_fast_path_hint_and_scalar_detection():
     assert _plan_for([prism, film("hBN", rotationZ=37.0), exit_("Calcite", rotationY=90)]).fast_path
     assert _plan_for([prism, film("MoO3", rotationY=180), exit_("Quartz", rotationY=90, rotationZ=12)]).fast_path
     assert not _plan_for([prism, film("hBN", rotationY=30), exit_("SiC")]).fast_path
+    # kernel hint: 1 = un-tilted (fast build), 2 = tilted with optically thin films (lean build), 0 = general
+    assert untilted.kernel_hint == 1
+    assert _plan_for([prism, film("hBN", rotationY=30), exit_("SiC")]).kernel_hint == 2
+    assert _plan_for([prism, film("hBN", rotationY=30, thickness=5.0), exit_("SiC")]).kernel_hint == 0
     assert not _plan_for([prism, film("hBN"), exit_("Quartz", rotationX=45)]).fast_path
     # an isotropic crystal may be tilted at will: R (eps I) R^T = eps I
     assert _plan_for([prism, film("hBN"), exit_("SiC", rotationY=33, rotationX=12)]).fast_path
