@@ -15,12 +15,12 @@ from tests.golden.payloads import ALL, BASELINE_SHAPES, angle_overrides
 pytestmark = pytest.mark.gpu
 
 
-def _run_gpu(name, backend, **kw):
+def _run_gpu(name, backend, device="cuda:0", device_tables=False, **kw):
     from hyperbolic_optics_b200 import Structure
 
     entry = ALL[name]
     inc, az = angle_overrides(entry)
-    s = Structure(device="cuda:0")
+    s = Structure(device=device, device_tables=device_tables)
     s.get_scenario(entry["payload"]["ScenarioData"])
     if inc is not None:
         s.scenario.incident_angle = inc
@@ -713,3 +713,29 @@ def test_device_side_material_tables(material, built_library):
     # a-few-ulp table differences are amplified at ill-conditioned points (TO poles, grazing angles)
     diff = np.abs(res[True] - res[False])[fin]
     assert diff.max() <= 1e-9 and np.median(diff) <= 1e-14
+
+
+def test_runs_on_the_device_that_owns_the_buffers(built_library):
+    """Structure(device="cuda:1") while cuda:0 is the current device: the library must launch on the
+    GPU that owns the tables and outputs (ho_engine.cu: DeviceScope), not on the current one."""
+    from hyperbolic_optics_b200 import Mueller
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    name = "multilayer_incident"
+    torch.cuda.set_device(0)
+    ref = _run_gpu(name, "transfer")
+    for keep in (False, True):
+        s = _run_gpu(name, "transfer", device="cuda:1", device_tables=True, keep_on_device=keep)
+        assert torch.cuda.current_device() == 0
+        if keep:
+            assert s.r_pp.device == torch.device("cuda:1")
+        got = s.r_pp.cpu().numpy() if keep else s.r_pp
+        fin = np.isfinite(ref.r_pp)
+        np.testing.assert_allclose(got[fin], ref.r_pp[fin], rtol=0, atol=1e-11)   # device-side tables: a few ulp
+        m = Mueller(s)
+        m.set_incident_polarization("linear", angle=45)
+        m.add_optical_component("anisotropic_sample")
+        s0 = m.get_all_parameters()["S0"]
+        assert np.isfinite(np.asarray(s0.cpu() if keep else s0)[fin]).all()
+    assert s.transfer_matrix.shape[-2:] == (4, 4)
