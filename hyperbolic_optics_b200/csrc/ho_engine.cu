@@ -152,7 +152,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     if (L.kind == HO_ANISO_EXIT) {
       substrate_plane(D, s, y0, y1);
       if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
-    } else {
+    } else if constexpr (FAST != 1) {   // (the fast build has left every crystal film above)
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       const cx<T> c = mk<T>(T(0), -(k0 * d));
       if (STABLE) film_stable<T, NM, FAST>(D, s, c, y0, y1, w, bail);
