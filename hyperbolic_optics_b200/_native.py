@@ -12,7 +12,7 @@ from pathlib import Path
 
 HO_MAX_LAYERS = 24
 HO_MAX_PEERS = 15
-HO_ABI_VERSION = 13
+HO_ABI_VERSION = 14
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -32,6 +32,7 @@ class LayerDesc(C.Structure):
         ("cos_beta", C.c_void_p), ("sin_beta", C.c_void_p), ("thickness", C.c_void_p),
         ("iso_eps", c128), ("iso_mu", c128),
         ("exit_cos", C.c_void_p), ("exit_n", C.c_double),
+        ("eps_ordinary", C.c_void_p),
     ]
 
 

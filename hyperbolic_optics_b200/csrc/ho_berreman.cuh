@@ -279,14 +279,21 @@ template <typename T> __device__ __forceinline__ cx<T> forward_sqrt(cx<T> y) {
 }
 
 // charpoly -> start values -> Bairstow polish of the forward quadratic factor.
-// Start values: when the odd coefficients are negligible (z is a principal axis of the rotated
-// tensors up to the reference's hidden 1e-8 angle offsets -- every un-tilted crystal) the quartic
-// is a perturbed biquadratic and the forward pair comes from three square roots; otherwise
-// Ferrari + classification.  A biquadratic start that fails to converge falls back to Ferrari.
+// Start values, cheapest first:
+//  * odd coefficients negligible (z is a principal axis of the rotated tensors up to the reference's
+//    hidden 1e-8 angle offsets -- every un-tilted crystal): the quartic is a perturbed biquadratic and
+//    the forward pair comes from three square roots;
+//  * uniaxial crystal (`uni`, any orientation; q_o = kx^2 - mu eps_o from ho_layer_t.eps_ordinary): the
+//    quartic factorises exactly into the ordinary and the extraordinary quadratic,
+//    (x^2 + q_o)(x^2 + c3 x + q_e) with q_e = c2 - q_o: two square roots, then the reference's
+//    forward rule on the four roots;
+//  * otherwise Ferrari / Cardano + the forward rule.
+// A start that fails the convergence check of the polish falls through to the next one.
 // FAST == 1 (fast-path kernel): only the biquadratic start is compiled; a point that would need
-// Ferrari sets `bail` and is finished later by the general kernel.  FAST == 2 (lean kernel for
+// more sets `bail` and is finished later by the general kernel.  FAST == 2 (lean kernel for
 // tilted stacks): the general start values, as FAST == 0.
-template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail) {
+template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail,
+                                                                                    bool uni = false, cx<T> qo = cx<T>{T(0), T(0)}) {
   const T tau4 = T(1e-20);
   T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
   bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
@@ -301,7 +308,7 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
     bail = bail || !biq || !ok;
   } else {
 #pragma unroll 1
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
       if (biq) {
         cx<T> y0, y1;
         quad_roots(c2, c0, y0, y1);
@@ -310,7 +317,13 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
         v = m0 * m1;
       } else {
         cx<T> lam[4];
-        start_roots(c3, c2, c1, c0, lam);
+        if (uni) {
+          lam[0] = csqrt(-qo);
+          lam[1] = -lam[0];
+          quad_roots(c3, c2 - qo, lam[2], lam[3]);
+        } else {
+          start_roots(c3, c2, c1, c0, lam);
+        }
         bool fwd[4];
         classify(lam, fwd);
         cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
@@ -322,8 +335,8 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
         v = pf;
       }
       bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
-      if (ok || !biq) break;
-      biq = false;
+      if (ok || !(biq || uni)) break;
+      if (biq) biq = false; else uni = false;
     }
   }
   Spectrum<T> s;
@@ -403,48 +416,100 @@ template <typename T> __device__ __forceinline__ void block_exp_apply(cx<T> lam_
   o1 = axpy(dd, r1, scale(phi_s, z1));
 }
 
-// cosh(z) and sinh(z)/z.  Below |z| = 1 both are evaluated by their Taylor series in z^2 (Horner
-// with real coefficients 1/(2k)!, 1/(2k+1)!: 9 complex FMAs each, truncation < 4e-19, no cancellation
-// in e^z - e^-z, no 0/0) -- cheaper than one complex exponential plus two reciprocals, and for an
-// optically thin film (|c mu| = k0 d |mu| << 1: BASELINE C4's 0.1 um hBN) it is the path nearly every
-// point takes, so warps do not diverge on the switch.
-template <typename T> __device__ __forceinline__ void cosh_sinhc(cx<T> z, cx<T>& ch, cx<T>& shc) {
-  if (norm2(z) < T(1)) {
-    const cx<T> z2 = z * z;
-    auto re = [](double c) { return mk<T>(T(c), T(0)); };
-    cx<T> a = re(1.0 / 6402373705728000.0), b = re(1.0 / 121645100408832000.0);   // 1/18!, 1/19!
-    a = fma(z2, a, re(1.0 / 20922789888000.0));  b = fma(z2, b, re(1.0 / 355687428096000.0));   // 1/16!, 1/17!
-    a = fma(z2, a, re(1.0 / 87178291200.0));     b = fma(z2, b, re(1.0 / 1307674368000.0));     // 1/14!, 1/15!
-    a = fma(z2, a, re(1.0 / 479001600.0));       b = fma(z2, b, re(1.0 / 6227020800.0));        // 1/12!, 1/13!
-    a = fma(z2, a, re(1.0 / 3628800.0));         b = fma(z2, b, re(1.0 / 39916800.0));          // 1/10!, 1/11!
-    a = fma(z2, a, re(1.0 / 40320.0));           b = fma(z2, b, re(1.0 / 362880.0));            // 1/8!, 1/9!
-    a = fma(z2, a, re(1.0 / 720.0));             b = fma(z2, b, re(1.0 / 5040.0));              // 1/6!, 1/7!
-    a = fma(z2, a, re(1.0 / 24.0));              b = fma(z2, b, re(1.0 / 120.0));               // 1/4!, 1/5!
-    a = fma(z2, a, re(0.5));                     b = fma(z2, b, re(1.0 / 6.0));                 // 1/2!, 1/3!
-    ch = fma(z2, a, re(1.0));
-    shc = fma(z2, b, re(1.0));
+// cosh(z) and sinh(z)/z as functions of w = z^2: both are entire in w, so neither a complex square
+// root nor a branch choice is needed.  Below |w| = 1 they are evaluated by their Taylor series in w
+// (Horner with real coefficients 1/(2k)!, 1/(2k+1)!: 9 steps each, truncation < 4e-19, no
+// cancellation in e^z - e^-z, no 0/0) -- cheaper than one complex exponential plus two reciprocals,
+// and for an optically thin film (|c mu| = k0 d |mu| << 1: BASELINE C4's 0.1 um hBN) it is the path
+// nearly every point takes, so warps do not diverge on the switch.
+// 1/(2k)! and 1/(2k+1)!, k = 9 .. 0 (literal arguments: the unrolled callers fold them to immediates)
+__host__ __device__ constexpr double cosh_coef(int i) {
+  return i == 0 ? 1.0 / 6402373705728000.0 : i == 1 ? 1.0 / 20922789888000.0 : i == 2 ? 1.0 / 87178291200.0 : i == 3 ? 1.0 / 479001600.0
+       : i == 4 ? 1.0 / 3628800.0 : i == 5 ? 1.0 / 40320.0 : i == 6 ? 1.0 / 720.0 : i == 7 ? 1.0 / 24.0 : i == 8 ? 0.5 : 1.0;
+}
+__host__ __device__ constexpr double sinhc_coef(int i) {
+  return i == 0 ? 1.0 / 121645100408832000.0 : i == 1 ? 1.0 / 355687428096000.0 : i == 2 ? 1.0 / 1307674368000.0 : i == 3 ? 1.0 / 6227020800.0
+       : i == 4 ? 1.0 / 39916800.0 : i == 5 ? 1.0 / 362880.0 : i == 6 ? 1.0 / 5040.0 : i == 7 ? 1.0 / 120.0 : i == 8 ? 1.0 / 6.0 : 1.0;
+}
+constexpr int kCoshTerms = 10;
+// one Horner step with a real constant term: w * a + k
+template <typename T> __device__ __forceinline__ cx<T> horner_step(cx<T> w, cx<T> a, double k) {
+  return mk<T>(::fma(w.re, a.re, ::fma(-w.im, a.im, T(k))), ::fma(w.re, a.im, w.im * a.re));
+}
+// first step: the leading coefficient is real
+template <typename T> __device__ __forceinline__ cx<T> horner_first(cx<T> w, double k1, double k0) {
+  return mk<T>(::fma(T(k1), w.re, T(k0)), T(k1) * w.im);
+}
+template <typename T> __device__ __forceinline__ void cosh_sinhc_series(cx<T> w, cx<T>& ch, cx<T>& shc) {
+  ch = horner_first(w, cosh_coef(0), cosh_coef(1));
+  shc = horner_first(w, sinhc_coef(0), sinhc_coef(1));
+#pragma unroll
+  for (int i = 2; i < kCoshTerms; ++i) { ch = horner_step(w, ch, cosh_coef(i)); shc = horner_step(w, shc, sinhc_coef(i)); }
+}
+// the same for two arguments at once: four independent Horner chains for the FP64 pipe to interleave
+template <typename T> __device__ __forceinline__ void cosh_sinhc_series2(cx<T> w0, cx<T> w1, cx<T>& ch0, cx<T>& shc0, cx<T>& ch1, cx<T>& shc1) {
+  ch0 = horner_first(w0, cosh_coef(0), cosh_coef(1));   ch1 = horner_first(w1, cosh_coef(0), cosh_coef(1));
+  shc0 = horner_first(w0, sinhc_coef(0), sinhc_coef(1)); shc1 = horner_first(w1, sinhc_coef(0), sinhc_coef(1));
+#pragma unroll
+  for (int i = 2; i < kCoshTerms; ++i) {
+    ch0 = horner_step(w0, ch0, cosh_coef(i)); ch1 = horner_step(w1, ch1, cosh_coef(i));
+    shc0 = horner_step(w0, shc0, sinhc_coef(i)); shc1 = horner_step(w1, shc1, sinhc_coef(i));
+  }
+}
+template <typename T> __device__ __forceinline__ void cosh_sinhc_w(cx<T> w, cx<T>& ch, cx<T>& shc) {
+  if (norm2(w) < T(1)) {
+    cosh_sinhc_series(w, ch, shc);
   } else {
+    cx<T> z = csqrt(w);
     cx<T> e = cexp(z), ei = recip(e);
     ch = T(0.5) * (e + ei);
     shc = (T(0.5) * (e - ei)) * recip(z);
   }
 }
 
-// Root pair m +- h of x^2 - s x + p and the growth max |Re(c lambda)| of its two modes
-template <typename T> __device__ __forceinline__ void pair_center(cx<T> s, cx<T> p, cx<T> c, cx<T>& m, cx<T>& h, T& growth) {
-  m = T(0.5) * s;
-  h = csqrt(fma(m, m, -p));
-  growth = ho_abs((c * m).re) + ho_abs((c * h).re);
+// both root pairs of a film: four interleaved series when both arguments are small (the usual case)
+template <typename T> __device__ __forceinline__ void cosh_sinhc_pair(cx<T> w0, cx<T> w1, cx<T>& A0, cx<T>& S0, cx<T>& A1, cx<T>& S1) {
+  if (norm2(w0) < T(1) && norm2(w1) < T(1)) {
+    cosh_sinhc_series2(w0, w1, A0, S0, A1, S1);
+  } else {   // rare (|c mu| >= 1): one rolled instance of the general evaluation keeps the code small
+    cx<T> ww[2] = {w0, w1}, AA[2], SS[2];
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) cosh_sinhc_w(ww[i], AA[i], SS[i]);
+    A0 = AA[0]; S0 = SS[0]; A1 = AA[1]; S1 = SS[1];
+  }
 }
-// Linear interpolant of exp(c x) on the pair, centred form alpha(x) = ph + dd (x - m) with
-// ph = e^{cm} cosh(ch), dd = e^{cm} c sinh(ch)/(ch): entire and even in h -- no ordering of the two
-// modes, one exponential (plus a series while |ch| < 1) instead of two
-template <typename T> __device__ __forceinline__ void pair_thin(cx<T> m, cx<T> h, cx<T> c, cx<T>& ph, cx<T>& dd) {
-  cx<T> A, S;
-  cosh_sinhc(c * h, A, S);
-  cx<T> e = cexp(c * m);
-  ph = e * A;
-  dd = e * (c * S);
+
+// Thin-film switch of both recursions: every mode of the pair m +- h has |Re(c lambda)| below the
+// limit.  The cubic mixes the four exponentials and costs log10 of their ratio in digits: e^6 (2.6
+// of 16 digits) in complex128, e^3 (1.3 of 7) in the opt-in complex64 kernels.
+// Given Re(c m) and w = (c h)^2 the test |Re(c m)| + |Re sqrt(w)| < limit is evaluated without the
+// square root: |Re sqrt(w)| = sqrt((|w| + Re w) / 2) < L  <=>  |w| < 2 L^2 - Re w.
+template <typename T> __device__ __forceinline__ bool thin_pair(T re_cm, cx<T> w) {
+  const T limit = sizeof(T) == 8 ? T(3) : T(1.5);
+  const T lim = limit - ho_abs(re_cm);
+  const T r = ::fma(T(2) * lim, lim, -w.re);
+  return lim > T(0) && r > T(0) && norm2(w) < r * r;
+}
+// Linear interpolants of exp(c x) on the two root pairs m +- h of a thin film, centred form
+// alpha(x) = ph + dd (x - m) with ph = e^{cm} cosh(ch), dd = e^{cm} c sinh(ch)/(ch): entire and even in
+// h -- no ordering of the two modes, no square root, one exponential per pair (plus a series while
+// |ch| < 1) instead of two.  cm = c m, w = (c h)^2 = c^2 (m^2 - p).
+// SCALE_FREE (no power / transmission outputs): the running plane is only defined up to a common
+// scalar, so the factor e^{c m_b} is dropped from both interpolants and ONE complex exponential,
+// e^{c (m_f - m_b)}, is left.
+template <typename T, bool SCALE_FREE> __device__ __forceinline__ void thin_pairs(cx<T> cmf, cx<T> wf, cx<T> cmb, cx<T> wb, cx<T> c,
+                                                                            cx<T>& phf, cx<T>& ddf, cx<T>& phb, cx<T>& ddb) {
+  cx<T> Af, Sf, Ab, Sb;
+  cosh_sinhc_pair(wf, wb, Af, Sf, Ab, Sb);
+  if constexpr (SCALE_FREE) {
+    cx<T> e = cexp(cmf - cmb);
+    phf = e * Af; ddf = e * (c * Sf);
+    phb = Ab;     ddb = c * Sb;
+  } else {
+    cx<T> ef = cexp(cmf), eb = cexp(cmb);
+    phf = ef * Af; ddf = ef * (c * Sf);
+    phb = eb * Ab; ddb = eb * (c * Sb);
+  }
 }
 
 // Coefficients of E(x) = alpha_b(x) + (alpha_f(x) - alpha_b(x)) q_b(x) h(x) mod q_f(x) q_b(x), with
@@ -460,14 +525,6 @@ template <typename T> __device__ __forceinline__ void cubic_coeffs(const Spectru
   a2 = fma(g2, s.pb - c2, fnma(s.sb, g1, g0));
   a1 = fnma(g2, c1, fma(s.pb, g1, fnma(s.sb, g0, ddb)));
   a0 = fnma(g2, c0, fma(s.pb, g0, ab0));
-}
-
-// Thin-film switch of both recursions: all four |Re(c lambda)| below this.  The cubic mixes the four
-// exponentials and costs log10 of their ratio in digits: e^6 (2.6 of 16 digits) in complex128,
-// e^3 (1.3 of 7) in the opt-in complex64 kernels.
-template <typename T> __device__ __forceinline__ bool thin_film(T gf, T gb) {
-  const T limit = sizeof(T) == 8 ? T(3) : T(1.5);
-  return gf < limit && gb < limit;
 }
 
 // y <- (a0 + a1 D + a2 D^2 + a3 D^3) y: three mat-vecs, one accumulator
@@ -488,18 +545,17 @@ template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const
 // no projected intermediates.  Mixing all four exponentials in one polynomial costs log10 of their
 // ratio in digits (<= 2.6 here); thick films -- where that form loses the sub-dominant growing
 // mode, SURVEY 7.0-6a -- keep the invariant-subspace block form.
-template <typename T, bool NM, int FAST = 0> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+template <typename T, bool NM, int FAST = 0, bool SCALE_FREE = false> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
-  cx<T> lf, phf, ddf, lb, phb, ddb;
+  cx<T> lf = T(0.5) * s.sf, lb = T(0.5) * s.sb, phf, ddf, phb, ddb;   // centres of the two root pairs
+  const cx<T> cc = c * c, cmf = c * lf, cmb = c * lb;
+  const cx<T> wf = cc * fma(lf, lf, -s.pf), wb = cc * fma(lb, lb, -s.pb);   // (c x half-distance)^2
   T gf, gb;
-  pair_center(s.sf, s.pf, c, lf, phf, gf);   // (phf, phb hold the half-distances of the pairs for now)
-  pair_center(s.sb, s.pb, c, lb, phb, gb);
   w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
-  if (thin_film(gf, gb)) {
+  if (thin_pair(cmf.re, wf) && thin_pair(cmb.re, wb)) {
     cx<T> a0, a1, a2, a3;
-    pair_thin(lf, phf, c, phf, ddf);
-    pair_thin(lb, phb, c, phb, ddb);
+    thin_pairs<T, SCALE_FREE>(cmf, wf, cmb, wb, c, phf, ddf, phb, ddb);
     cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
     cubic_apply(D, a0, a1, a2, a3, y0);
     cubic_apply(D, a0, a1, a2, a3, y1);
@@ -588,12 +644,12 @@ template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs
   s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   // pair 0
   cx<T> d0 = T(0.5) * s.sf, d1 = T(0.5) * s.sb;
-  cx<T> z0 = c * csqrt(fma(d0, d0, -s.pf)), z1 = c * csqrt(fma(d1, d1, -s.pb));
+  const cx<T> cc = c * c;
+  cx<T> w0 = cc * fma(d0, d0, -s.pf), w1 = cc * fma(d1, d1, -s.pb);   // (c mu_i)^2
   cx<T> x0 = c * d0, x1 = c * d1;
-  if (!(thin_film(ho_abs(z0.re), ho_abs(z1.re)) && norm2(x0) < T(1e-10) && norm2(x1) < T(1e-10))) return false;
+  if (!(thin_pair(T(0), w0) && thin_pair(T(0), w1) && norm2(x0) < T(1e-10) && norm2(x1) < T(1e-10))) return false;
   cx<T> A0, S0, A1, S1;
-  cosh_sinhc(z0, A0, S0);
-  cosh_sinhc(z1, A1, S1);
+  cosh_sinhc_pair(w0, w1, A0, S0, A1, S1);
   const cx<T> one = mk<T>(T(1), T(0));
   cx<T> e0 = fma(T(0.5) * x0, x0, one + x0), e1 = fma(T(0.5) * x1, x1, one + x1);  // e^{c delta}, |c delta| < 1e-5
   cx<T> h0, h1;
@@ -617,7 +673,7 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 // Renormalises so that rows (Ex, Ey) of the forward part are the identity.
 // w[0..3] = (w00, w01, w10, w11): the 2x2 map W with Y_new = exp(cD) Y_old W, i.e. coordinates at
 // the top of the film -> coordinates at its bottom (used by the power bookkeeping only).
-template <typename T, bool NM, int FAST = 0> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+template <typename T, bool NM, int FAST = 0, bool SCALE_FREE = false> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   // Thin film (all four |Re(c lambda)| < 3): nothing can overflow and the four exponentials are
@@ -625,14 +681,13 @@ template <typename T, bool NM, int FAST = 0> __device__ __forceinline__ void fil
   // transfer recursion and only re-based to unit (Ex, Ey) rows afterwards -- the re-basing keeps
   // the basis well conditioned, so the <= 2.6 digits the cubic costs do not compound over
   // layers.  W is the re-basing matrix.
-  cx<T> lf, phf, ddf, lb, phb, ddb;
+  cx<T> lf = T(0.5) * s.sf, lb = T(0.5) * s.sb, phf, ddf, phb, ddb;   // centres of the two root pairs
+  const cx<T> cc = c * c, cmf = c * lf, cmb = c * lb;
+  const cx<T> wf = cc * fma(lf, lf, -s.pf), wb = cc * fma(lb, lb, -s.pb);   // (c x half-distance)^2
   T gf, gb;
-  pair_center(s.sf, s.pf, c, lf, phf, gf);   // (phf, phb hold the half-distances of the pairs for now)
-  pair_center(s.sb, s.pb, c, lb, phb, gb);
-  if (thin_film(gf, gb)) {
+  if (thin_pair(cmf.re, wf) && thin_pair(cmb.re, wb)) {
     cx<T> a0, a1, a2, a3;
-    pair_thin(lf, phf, c, phf, ddf);
-    pair_thin(lb, phb, c, phb, ddb);
+    thin_pairs<T, SCALE_FREE>(cmf, wf, cmb, wb, c, phf, ddf, phb, ddb);
     cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
     cubic_apply(D, a0, a1, a2, a3, y0);
     cubic_apply(D, a0, a1, a2, a3, y1);
@@ -716,7 +771,7 @@ template <typename T> __device__ __forceinline__ void iso_film(T k, cx<T> eps, c
   if (!stable) {
     // exp(c D) = cosh(c kz) I + c sinhc(c kz) D  (even in kz: no branch choice needed)
     cx<T> A, S;
-    cosh_sinhc(c * csqrt(kz2), A, S);
+    cosh_sinhc_w((c * c) * kz2, A, S);
     cx<T> B = c * S;
     y0 = axpy(B, dy0, scale(A, y0));
     y1 = axpy(B, dy1, scale(A, y1));

@@ -148,15 +148,25 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
       if (!general) return;
       if constexpr (FAST == 1) { bail = true; return; }
     }
-    Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail);
+    // uniaxial crystal with scalar mu: q_o = kx^2 - mu eps_o of the exact ordinary factor (start values only)
+    bool uni = false;
+    cx<T> qo = mk<T>(T(0), T(0));
+    if constexpr (NM && FAST != 1 && sizeof(T) == 8) {
+      if (L.eps_ordinary != nullptr) {
+        uni = true;
+        const cx<T> eo = ldc<T>(L.eps_ordinary + (L.n_eps > 1 ? f : 0)), mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
+        qo = fnma(mu, eo, mk<T>(k * k, T(0)));
+      }
+    }
+    Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail, uni, qo);
     if (L.kind == HO_ANISO_EXIT) {
       substrate_plane(D, s, y0, y1);
       if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
     } else if constexpr (FAST != 1) {   // (the fast build has left every crystal film above)
       const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
       const cx<T> c = mk<T>(T(0), -(k0 * d));
-      if (STABLE) film_stable<T, NM, FAST>(D, s, c, y0, y1, w, bail);
-      else film_transfer<T, NM, FAST>(D, s, c, y0, y1, w, bail);
+      if (STABLE) film_stable<T, NM, FAST, !EXTRAS>(D, s, c, y0, y1, w, bail);
+      else film_transfer<T, NM, FAST, !EXTRAS>(D, s, c, y0, y1, w, bail);
     }
   }
 }

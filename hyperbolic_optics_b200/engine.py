@@ -85,6 +85,8 @@ class DeviceProblem:
                 L.n_eps, L.n_mu, L.n_beta = lp.eps.shape[0], lp.mu.shape[0], lp.cos_beta.size
                 layer_slots += [(i, "eps", self._put_c128(lp.eps)), (i, "mu", self._put_c128(lp.mu)),
                                 (i, "cos_beta", self._put_f64(lp.cos_beta)), (i, "sin_beta", self._put_f64(lp.sin_beta))]
+                if lp.eps_ordinary is not None:
+                    layer_slots.append((i, "eps_ordinary", self._put_c128(lp.eps_ordinary)))
             if lp.thickness is not None:
                 L.n_thickness = lp.thickness.size
                 layer_slots.append((i, "thickness", self._put_f64(lp.thickness)))

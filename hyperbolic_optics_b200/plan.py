@@ -48,6 +48,7 @@ class LayerPlan:
     mu: np.ndarray | None = None       # [Fm, 6] complex128, Fm in {1, F}
     mu_scalar: bool = True             # mu proportional to identity (rotation-invariant)
     eps_scalar: bool = False           # eps proportional to identity at every frequency (isotropic crystal)
+    eps_ordinary: np.ndarray | None = None  # [Fe] complex128: ordinary principal value of a uniaxial crystal (start-value hint)
     cos_beta: np.ndarray | None = None  # [Bb] float64, Bb in {1, B}
     sin_beta: np.ndarray | None = None
     thickness: np.ndarray | None = None  # [Tt] float64 cm, Tt in {1, T}
@@ -221,6 +222,7 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
                 lp = LayerPlan(KIND_ANISO_EXIT, kind)
             lp.eps, lp.mu, lp.mu_scalar = np.ascontiguousarray(eps), np.ascontiguousarray(mu), mu_scalar
             lp.eps_scalar = eps_scalar
+            lp.eps_ordinary = None if eps_scalar or not mu_scalar else _ordinary_value(eps_packed)
             lp.cos_beta, lp.sin_beta, lp.material = cos_b, sin_b, material
             lp.rotation_xy = np.eye(3) if eps_scalar else q
         elif kind == TYPE_ISO_EXIT:
@@ -248,6 +250,20 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
     elif crystals and all(_optically_thin(lp, plan.k0_all) for lp in crystals if lp.kind == KIND_ANISO_FILM):
         plan.kernel_hint = 2
     return plan
+
+
+def _ordinary_value(eps_packed):
+    """``[Fe]`` ordinary principal value when the un-rotated tensor is diagonal with the same two
+    equal entries at every frequency (uniaxial crystal: Quartz, Calcite, Sapphire, hBN, or an
+    arbitrary diagonal tensor of that shape), else ``None``.  Rotations keep the property, so the
+    kernel may factorise the characteristic quartic of the rotated tensor (``ho_layer_t.eps_ordinary``)."""
+    if np.any(eps_packed[:, [1, 2, 4]] != 0):
+        return None
+    xx, yy, zz = eps_packed[:, 0], eps_packed[:, 3], eps_packed[:, 5]
+    for same, value in ((xx == yy, xx), (xx == zz, xx), (yy == zz, yy)):
+        if np.all(same):
+            return np.ascontiguousarray(value, dtype=np.complex128)
+    return None
 
 
 def _optically_thin(lp, k0) -> bool:

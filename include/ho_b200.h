@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 13
+#define HO_ABI_VERSION 14
 #define HO_MAX_LAYERS 24
 #define HO_MAX_PEERS 15
 
@@ -75,6 +75,14 @@ typedef struct {
   ho_c128 iso_eps, iso_mu; /* HO_ISO_FILM scalars (layers.py:484-523) */
   const ho_c128* exit_cos; /* HO_ISO_EXIT: cos(theta_f)[A], complex principal root (layers.py:190-238) */
   double exit_n;           /* HO_ISO_EXIT: sqrt(eps_exit) */
+  /* Uniaxial crystal (two equal principal values eps_o, any orientation; scalar mu): the ordinary
+     principal value per frequency, [n_eps], else NULL.  A performance hint only: the characteristic
+     quartic of such a medium factorises exactly into the ordinary and the extraordinary quadratic,
+       (x^2 + kx^2 - mu eps_o) (x^2 + c3 x + q_e),
+     so the start values of the spectral split are two square roots instead of the Ferrari / Cardano
+     closed form (np.linalg.eig in the reference, waves.py:256-296).  The polish and its convergence
+     check are the same; a failed check falls back to the general start values. */
+  const ho_c128* eps_ordinary;
 } ho_layer_t;
 
 enum ho_kernel_hint { HO_HINT_NONE = 0, HO_HINT_UNTILTED = 1, HO_HINT_TILTED_THIN = 2 };

@@ -264,6 +264,24 @@ def test_fast_path_hint_and_scalar_detection():
     assert _plan_for([prism, film("hBN", rotationY=30), exit_("SiC")]).kernel_hint == 2
     assert _plan_for([prism, film("hBN", rotationY=30, thickness=5.0), exit_("SiC")]).kernel_hint == 0
     assert not _plan_for([prism, film("hBN"), exit_("Quartz", rotationX=45)]).fast_path
+    # uniaxial crystals carry their ordinary principal value (start values of the spectral split: the
+    # quartic of a uniaxial medium factorises); biaxial / monoclinic / isotropic ones do not
+    tilted = _plan_for([prism, film("hBN", rotationY=30, rotationZ=10), exit_("Quartz", rotationY=50)])
+    for lp, name in zip(tilted.layers, ("hBN", "Quartz")):
+        eo = materials.create_material(name).eps_packed(tilted.frequency)[:, 0]
+        np.testing.assert_array_equal(lp.eps_ordinary, eo)
+        # ... and the factorisation holds for the rotated table: det(x - Delta) = (x^2 + q_o)(x^2 + c3 x + q_e)
+        e = materials.unpack_symmetric(lp.eps)[7]
+        k = 1.3
+        delta = np.array([[-k * e[0, 2] / e[2, 2], -k * e[1, 2] / e[2, 2], 0, 1 - k * k / e[2, 2]], [0, 0, -1, 0],
+                          [e[1, 2] * e[0, 2] / e[2, 2] - e[0, 1], e[1, 2] ** 2 / e[2, 2] - e[1, 1] + k * k, 0, k * e[1, 2] / e[2, 2]],
+                          [e[0, 0] - e[0, 2] ** 2 / e[2, 2], -(e[1, 2] * e[0, 2] / e[2, 2] - e[0, 1]), 0, -k * e[0, 2] / e[2, 2]]])
+        c = np.poly(delta)
+        qo = k * k - eo[7]
+        assert abs(c[3] - c[1] * qo) <= 1e-12 * abs(c[3]) + 1e-12 and abs(c[4] - qo * (c[2] - qo)) <= 1e-12 * abs(c[4]) + 1e-12
+    assert untilted.layers[1].eps_ordinary is None                       # SiC: isotropic
+    assert _plan_for([prism, film("MoO3", rotationY=20), exit_("SiC")]).layers[0].eps_ordinary is None   # biaxial
+    assert _plan_for([prism, film("hBN"), exit_("GalliumOxide", rotationY=20)]).layers[1].eps_ordinary is None   # monoclinic
     # an isotropic crystal may be tilted at will: R (eps I) R^T = eps I
     assert _plan_for([prism, film("hBN"), exit_("SiC", rotationY=33, rotationX=12)]).fast_path
     # no crystal at all: nothing to hint against

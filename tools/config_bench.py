@@ -45,6 +45,10 @@ def configs():
         "c4_tilted": ({"type": "FullSweep", "frequency": f410},
                       [P.prism(12.5), P.film("hBN", 0.1, ry=30, rz=10), P.substrate("Quartz", ry=50)], 512, 480,
                       ("transfer", "scattering"), False),
+        # biaxial film and exit, tilted: no uniaxial factorisation -> Ferrari / Cardano start values on both layers
+        "c4_tilted_biaxial": ({"type": "FullSweep", "frequency": f410},
+                              [P.prism(12.5), P.film("MoO3", 0.1, ry=30, rz=10), P.substrate("MoO3", ry=50)], 512, 480,
+                              ("transfer", "scattering"), False),
         "c4_power": ({"type": "FullSweep", "frequency": f410[::4]},
                      [P.prism(12.5), P.film("hBN", 0.1), P.substrate("SiC")], 512, 480, ("scattering",), True),
         "c5": ({"type": "Incident", "frequency": list(np.linspace(500.0, 1050.0, 64))}, c5_full, 90, None,

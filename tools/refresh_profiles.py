@@ -28,10 +28,13 @@ def main():
     args = ap.parse_args()
     g, p = ROOT / "gpurun_out", ROOT / "profiles"
     rep = g / f"{args.stem}.ncu-rep"
+    if not rep.exists():   # pages exported on the GPU box by tools/ncu_round.sh
+        rep = g / f"{args.stem}_raw.csv"
     subprocess.run([sys.executable, str(ROOT / "tools/summarize_ncu.py"), str(rep), str(p / f"{args.tag}_full"), str(args.points)],
                    check=True, stdout=subprocess.DEVNULL)
-    src = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    (g / f"{args.stem}_source.csv").write_text(src)
+    if rep.suffix != ".csv":
+        src = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        (g / f"{args.stem}_source.csv").write_text(src)
     hist = subprocess.run([sys.executable, str(ROOT / "tools/ncu_sass_hist.py"), str(g / f"{args.stem}_source.csv")],
                           capture_output=True, text=True).stdout
     (p / f"{args.tag}_sass_histogram.txt").write_text(hist)

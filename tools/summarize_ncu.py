@@ -29,7 +29,10 @@ def to_bytes(value, unit):
 
 
 def main(rep, out_prefix, points):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):   # `ncu -i <rep> --page raw --csv` exported on the GPU box
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     launches = []
