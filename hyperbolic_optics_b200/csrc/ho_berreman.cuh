@@ -236,7 +236,10 @@ template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4
 // complementary factor lambda^2 + b1 lambda + b0 follows by deflation.  Per-point early exits:
 // the Newton step is skipped once the residual of the division is at rounding level, and the
 // loop ends once a step is negligible (accurate start values need exactly one step).
-template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0) {
+// accept_start: the start values may already be exact (uniaxial factorisation): the residual test
+// also applies before the first step.
+template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0,
+                                                              bool accept_start = false) {
   const T res_tol2 = sizeof(T) == 8 ? T(1e-28) : T(1e-12);
   const T step_tol2 = sizeof(T) == 8 ? T(1e-22) : T(1e-7);
   const int max_steps = 3;
@@ -248,7 +251,7 @@ template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c
     cx<T> t1 = u * b0, t2 = v * b1, t3 = v * b0;
     cx<T> r1 = c1 - t1 - t2;
     cx<T> r0 = c0 - t3;
-    if (it > 0 && norm2(r1) <= res_tol2 * (norm2(t1) + norm2(t2)) && norm2(r0) <= res_tol2 * norm2(t3)) { converged = true; break; }
+    if ((it > 0 || accept_start) && norm2(r1) <= res_tol2 * (norm2(t1) + norm2(t2)) && norm2(r0) <= res_tol2 * norm2(t3)) { converged = true; break; }
     if (it == max_steps) break;
     cx<T> umb = u - b1;
     cx<T> j22 = v - b0;
@@ -299,13 +302,24 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
   bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
   cx<T> u, v, b1, b0;
   if constexpr (FAST == 1) {
-    cx<T> y0, y1;
-    quad_roots(c2, c0, y0, y1);
-    cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
+    // (un-tilted plan: a uniaxial crystal keeps the ordinary / extraordinary root pairs +-mu_o and
+    // delta_e +- mu_e, the forward member of each by the reference's rule on the pair -- no ranking)
+    cx<T> y0, y1, m0, m1;
+    if (uni) {
+      m0 = forward_sqrt(-qo);
+      quad_roots(c3, c2 - qo, y0, y1);
+      const bool f0 = (ho_abs(y0.im) > T(1e-9)) ? (y0.im > T(0)) : (y0.re > T(0));
+      const bool f1 = (ho_abs(y1.im) > T(1e-9)) ? (y1.im > T(0)) : (y1.re > T(0));
+      m1 = f0 ? y0 : y1;
+      bail = bail || (f0 == f1);   // not one forward and one backward root: the general kernel ranks all four
+    } else {
+      quad_roots(c2, c0, y0, y1);
+      m0 = forward_sqrt(y0); m1 = forward_sqrt(y1);
+    }
     u = -(m0 + m1);
     v = m0 * m1;
-    bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
-    bail = bail || !biq || !ok;
+    bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0, uni);
+    bail = bail || !(biq || uni) || !ok;
   } else {
 #pragma unroll 1
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -334,7 +348,7 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
         u = -sf;
         v = pf;
       }
-      bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
+      bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0, !biq && uni);
       if (ok || !(biq || uni)) break;
       if (biq) biq = false; else uni = false;
     }

@@ -151,7 +151,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     // uniaxial crystal with scalar mu: q_o = kx^2 - mu eps_o of the exact ordinary factor (start values only)
     bool uni = false;
     cx<T> qo = mk<T>(T(0), T(0));
-    if constexpr (NM && FAST != 1 && sizeof(T) == 8) {
+    if constexpr (NM && sizeof(T) == 8) {
       if (L.eps_ordinary != nullptr) {
         uni = true;
         const cx<T> eo = ldc<T>(L.eps_ordinary + (L.n_eps > 1 ? f : 0)), mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
