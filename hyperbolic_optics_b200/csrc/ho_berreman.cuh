@@ -559,23 +559,43 @@ template <typename T, bool NM> __device__ __forceinline__ void cubic_apply(const
 // no projected intermediates.  Mixing all four exponentials in one polynomial costs log10 of their
 // ratio in digits (<= 2.6 here); thick films -- where that form loses the sub-dominant growing
 // mode, SURVEY 7.0-6a -- keep the invariant-subspace block form.
-template <typename T, bool NM, int FAST = 0, bool SCALE_FREE = false> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
-  cx<T> h0, h1;
-  projector_coeffs(s, h0, h1);
+// Coefficients of that cubic from the spectral split; false when the film is not thin.
+template <typename T, bool SCALE_FREE> __device__ __forceinline__ bool film_thin_coeffs(const Spectrum<T>& s, cx<T> c, cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
   cx<T> lf = T(0.5) * s.sf, lb = T(0.5) * s.sb, phf, ddf, phb, ddb;   // centres of the two root pairs
   const cx<T> cc = c * c, cmf = c * lf, cmb = c * lb;
   const cx<T> wf = cc * fma(lf, lf, -s.pf), wb = cc * fma(lb, lb, -s.pb);   // (c x half-distance)^2
+  if (!(thin_pair(cmf.re, wf) && thin_pair(cmb.re, wb))) return false;
+  cx<T> h0, h1;
+  projector_coeffs(s, h0, h1);
+  thin_pairs<T, SCALE_FREE>(cmf, wf, cmb, wb, c, phf, ddf, phb, ddb);
+  cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
+  return true;
+}
+
+// The cubic applied to the running plane; stable recursion: then re-based to unit (Ex, Ey) rows,
+// which keeps the basis well conditioned so that the <= 2.6 digits the cubic costs do not compound
+// over layers (W = the re-basing matrix, for the power bookkeeping).
+template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_cubic(const Delta<T, NM>& D, cx<T> a0, cx<T> a1, cx<T> a2, cx<T> a3,
+                                                                                Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
+  cubic_apply(D, a0, a1, a2, a3, y0);
+  cubic_apply(D, a0, a1, a2, a3, y1);
+  if constexpr (STABLE) {
+    inv2(y0.v0, y1.v0, y0.v1, y1.v1, w[0], w[1], w[2], w[3]);
+    Vec4<T> t0 = axpy(w[2], y1, scale(w[0], y0));
+    y1 = axpy(w[3], y1, scale(w[1], y0));
+    y0 = t0;
+  } else {
+    w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
+  }
+}
+
+// Thick film, transfer recursion: the invariant-subspace block form.
+template <typename T, bool NM> __device__ __forceinline__ void film_transfer_thick(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
+  cx<T> h0, h1;
+  projector_coeffs(s, h0, h1);
+  cx<T> lf, phf, ddf, lb, phb, ddb;
   T gf, gb;
   w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
-  if (thin_pair(cmf.re, wf) && thin_pair(cmb.re, wb)) {
-    cx<T> a0, a1, a2, a3;
-    thin_pairs<T, SCALE_FREE>(cmf, wf, cmb, wb, c, phf, ddf, phb, ddb);
-    cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
-    cubic_apply(D, a0, a1, a2, a3, y0);
-    cubic_apply(D, a0, a1, a2, a3, y1);
-    return;
-  }
-  if constexpr (FAST != 0) { bail = true; return; }  // thick film: left to the general kernel
   bool sepf, sepb;
   pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
   pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
@@ -622,50 +642,71 @@ template <typename T, bool NM, int FAST = 0, bool SCALE_FREE = false> __device__
 //        alpha_i(x) = e^{c delta_i} [cosh(c mu_i) + (x - delta_i) sinh(c mu_i) / mu_i],
 //      entire and even in mu_i: no forward/backward classification, one exponential per pair.
 //   3. the two interpolants are merged into one cubic by the projector formula of cubic_coeffs.
+// Uniaxial film (`uni`, q_o = kx^2 - mu eps_o; any orientation): the two pairs are known in closed
+// form -- the ordinary pair +-mu_o, mu_o^2 = -q_o, and the extraordinary pair delta_e +- mu_e of
+// x^2 + c3 x + q_e, q_e = c2 - q_o -- so steps 1 reduces to a consistency check of that
+// factorisation against the computed quartic (it also guards a wrong hint), and e^{c delta_e} is a
+// true exponential when the crystal is tilted (delta_e = -c3/2 not small).
 // Returns false when the point has to take the general path: odd coefficients not small, y0 ~ y1
 // (the merge would lose more than 3 digits: near-normal incidence on a c-cut uniaxial film),
 // polish not converged, or thick film (a |Re(c mu)| >= 3).
-template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c,
+// UNI_ONLY (lean kernel for tilted stacks): only the uniaxial closed form is compiled.
+template <typename T, bool UNI_ONLY = false> __device__ __forceinline__ bool pair_symmetric_film_coeffs(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c, bool uni, cx<T> qo,
                                                                                 cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
   const T odd_tol = sizeof(T) == 8 ? T(1e-12) : T(1e-6);
   const T step_tol = sizeof(T) == 8 ? T(1e-20) : T(1e-9);
-  T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
-  if (!((n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2)))) return false;
-  cx<T> y0, y1;
-  quad_roots(c2, c0, y0, y1);
-  cx<T> dy = y0 - y1;
-  if (!(norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1)))) return false;
-  cx<T> idy = recip(dy);
-  cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
-  // two steps; a third only where the second still moved (rate ~ tilt |mu| / |y0 - y1|: step k has
-  // size rate^k, the error after it rate^(k+1))
-  bool done = false;
+  Spectrum<T> s;
+  if (uni) {
+    const cx<T> qe = c2 - qo;
+    const cx<T> t1 = c3 * qo, t0 = qo * qe;
+    const T fac_tol = T(1e-24);   // |c1 - c3 q_o|, |c0 - q_o q_e| at rounding level
+    uni = norm2(c1 - t1) <= fac_tol * (norm2(t1) + norm2(c1)) && norm2(c0 - t0) <= fac_tol * norm2(t0);
+    s.sf = mk<T>(T(0), T(0)); s.pf = qo; s.sb = -c3; s.pb = qe;
+  }
+  if (!uni) {
+    if constexpr (UNI_ONLY) return false;
+    T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
+    if (!((n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2)))) return false;
+    cx<T> y0, y1;
+    quad_roots(c2, c0, y0, y1);
+    cx<T> dy = y0 - y1;
+    if (!(norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1)))) return false;
+    cx<T> idy = recip(dy);
+    cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
+    // two steps; a third only where the second still moved (rate ~ tilt |mu| / |y0 - y1|: step k has
+    // size rate^k, the error after it rate^(k+1))
+    bool done = false;
 #pragma unroll 1
-  for (int it = 0; it < 3 && !done; ++it) {
+    for (int it = 0; it < 3 && !done; ++it) {
+      b1 = c3 - u;
+      b0 = fnma(u, b1, c2 - v);
+      du = fnma(v, b1, fnma(u, b0, c1)) * idy;
+      dv = fnma(v, b0, c0) * idy;
+      u = u + du;
+      v = v + dv;
+      T nv = norm2(v), ndu = norm2(du);
+      done = it >= 1 && norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv;  // |du|^2 <= tol |v|
+    }
+    if (!done) return false;
     b1 = c3 - u;
     b0 = fnma(u, b1, c2 - v);
-    du = fnma(v, b1, fnma(u, b0, c1)) * idy;
-    dv = fnma(v, b0, c0) * idy;
-    u = u + du;
-    v = v + dv;
-    T nv = norm2(v), ndu = norm2(du);
-    done = it >= 1 && norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv;  // |du|^2 <= tol |v|
+    s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   }
-  if (!done) return false;
-  b1 = c3 - u;
-  b0 = fnma(u, b1, c2 - v);
-  Spectrum<T> s;
-  s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
-  // pair 0
-  cx<T> d0 = T(0.5) * s.sf, d1 = T(0.5) * s.sb;
+  cx<T> d0 = T(0.5) * s.sf, d1 = T(0.5) * s.sb;   // pair centres delta_i
   const cx<T> cc = c * c;
-  cx<T> w0 = cc * fma(d0, d0, -s.pf), w1 = cc * fma(d1, d1, -s.pb);   // (c mu_i)^2
+  cx<T> m0 = fma(d0, d0, -s.pf), m1 = fma(d1, d1, -s.pb);              // mu_i^2
+  // the merge of the two interpolants divides by the resultant ~ (mu_0^2 - mu_1^2)^2: y0 ~ y1 loses digits
+  if (!(norm2(m0 - m1) >= T(1e-6) * (norm2(m0) + norm2(m1)))) return false;
+  cx<T> w0 = cc * m0, w1 = cc * m1;   // (c mu_i)^2
   cx<T> x0 = c * d0, x1 = c * d1;
-  if (!(thin_pair(T(0), w0) && thin_pair(T(0), w1) && norm2(x0) < T(1e-10) && norm2(x1) < T(1e-10))) return false;
+  if (!(thin_pair(x0.re, w0) && thin_pair(x1.re, w1) && norm2(x0) < T(1e-10))) return false;
   cx<T> A0, S0, A1, S1;
   cosh_sinhc_pair(w0, w1, A0, S0, A1, S1);
   const cx<T> one = mk<T>(T(1), T(0));
-  cx<T> e0 = fma(T(0.5) * x0, x0, one + x0), e1 = fma(T(0.5) * x1, x1, one + x1);  // e^{c delta}, |c delta| < 1e-5
+  cx<T> e0 = fma(T(0.5) * x0, x0, one + x0), e1;  // e^{c delta}, |c delta| < 1e-5
+  if (norm2(x1) < T(1e-10)) e1 = fma(T(0.5) * x1, x1, one + x1);
+  else if (uni) e1 = cexp(x1);     // tilted uniaxial film
+  else return false;
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
   cubic_coeffs(s, h0, h1, d0, e0 * A0, e0 * (c * S0), d1, e1 * A1, e1 * (c * S1), a0, a1, a2, a3);
@@ -687,31 +728,11 @@ template <typename T> __device__ __forceinline__ Vec4<T> lin_apply(cx<T> phi, cx
 // Renormalises so that rows (Ex, Ey) of the forward part are the identity.
 // w[0..3] = (w00, w01, w10, w11): the 2x2 map W with Y_new = exp(cD) Y_old W, i.e. coordinates at
 // the top of the film -> coordinates at its bottom (used by the power bookkeeping only).
-template <typename T, bool NM, int FAST = 0, bool SCALE_FREE = false> __device__ __forceinline__ void film_stable(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+template <typename T, bool NM> __device__ __forceinline__ void film_stable_thick(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);
-  // Thin film (all four |Re(c lambda)| < 3): nothing can overflow and the four exponentials are
-  // within e^6 of each other, so the plane is propagated by the same cubic polynomial as in the
-  // transfer recursion and only re-based to unit (Ex, Ey) rows afterwards -- the re-basing keeps
-  // the basis well conditioned, so the <= 2.6 digits the cubic costs do not compound over
-  // layers.  W is the re-basing matrix.
-  cx<T> lf = T(0.5) * s.sf, lb = T(0.5) * s.sb, phf, ddf, phb, ddb;   // centres of the two root pairs
-  const cx<T> cc = c * c, cmf = c * lf, cmb = c * lb;
-  const cx<T> wf = cc * fma(lf, lf, -s.pf), wb = cc * fma(lb, lb, -s.pb);   // (c x half-distance)^2
+  cx<T> lf, phf, ddf, lb, phb, ddb;
   T gf, gb;
-  if (thin_pair(cmf.re, wf) && thin_pair(cmb.re, wb)) {
-    cx<T> a0, a1, a2, a3;
-    thin_pairs<T, SCALE_FREE>(cmf, wf, cmb, wb, c, phf, ddf, phb, ddb);
-    cubic_coeffs(s, h0, h1, lf, phf, ddf, lb, phb, ddb, a0, a1, a2, a3);
-    cubic_apply(D, a0, a1, a2, a3, y0);
-    cubic_apply(D, a0, a1, a2, a3, y1);
-    inv2(y0.v0, y1.v0, y0.v1, y1.v1, w[0], w[1], w[2], w[3]);
-    Vec4<T> t0 = axpy(w[2], y1, scale(w[0], y0));
-    y1 = axpy(w[3], y1, scale(w[1], y0));
-    y0 = t0;
-    return;
-  }
-  if constexpr (FAST != 0) { bail = true; return; }  // thick film: left to the general kernel
   bool sepf, sepb;
   pair_modes(s.sf, s.pf, c, lf, phf, ddf, sepf, gf);
   pair_modes(s.sb, s.pb, c, lb, phb, ddb, sepb, gb);
@@ -739,20 +760,11 @@ template <typename T, bool NM, int FAST = 0, bool SCALE_FREE = false> __device__
   w[2] = fma(n11, g0.v1, n10 * g0.v0); w[3] = fma(n11, g1.v1, n10 * g1.v0);
 }
 
-// Fast-path film: the pair-symmetric form above, then (stable recursion) the same re-basing as film_stable
-template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_pair_symmetric(const Delta<T, NM>& D, cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool& bail) {
+// exp(c D) Y with the exact scale, thin or thick (the materialising kernels of ho_modes.cuh)
+template <typename T, bool NM> __device__ __forceinline__ void film_transfer(const Delta<T, NM>& D, const Spectrum<T>& s, cx<T> c, Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
   cx<T> a0, a1, a2, a3;
-  if (!pair_symmetric_film_coeffs(c3, c2, c1, c0, c, a0, a1, a2, a3)) { bail = true; return; }
-  cubic_apply(D, a0, a1, a2, a3, y0);
-  cubic_apply(D, a0, a1, a2, a3, y1);
-  if constexpr (STABLE) {
-    inv2(y0.v0, y1.v0, y0.v1, y1.v1, w[0], w[1], w[2], w[3]);
-    Vec4<T> t0 = axpy(w[2], y1, scale(w[0], y0));
-    y1 = axpy(w[3], y1, scale(w[1], y0));
-    y0 = t0;
-  } else {
-    w[0] = mk<T>(T(1), T(0)); w[1] = mk<T>(T(0), T(0)); w[2] = w[1]; w[3] = w[0];
-  }
+  if (film_thin_coeffs<T, false>(s, c, a0, a1, a2, a3)) film_cubic<T, NM, false>(D, a0, a1, a2, a3, y0, y1, w);
+  else film_transfer_thick(D, s, c, y0, y1, w);
 }
 
 // Forward invariant subspace of a semi-infinite crystal: q_b(D) [e0 e1], q_b(x) = x^2 - s_b x + p_b.

@@ -140,15 +140,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
     cx<T> c3, c2, c1, c0;
     charpoly(D, c3, c2, c1, c0);
-    if (L.kind == HO_ANISO_FILM && (FAST == 1 || (FAST == 0 && untilted))) {
-      // un-tilted thin crystal film: pair-symmetric closed form, no spectral split
-      const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-      bool general = false;
-      film_pair_symmetric<T, NM, STABLE>(D, c3, c2, c1, c0, mk<T>(T(0), -(k0 * d)), y0, y1, w, general);
-      if (!general) return;
-      if constexpr (FAST == 1) { bail = true; return; }
-    }
-    // uniaxial crystal with scalar mu: q_o = kx^2 - mu eps_o of the exact ordinary factor (start values only)
+    // uniaxial crystal with scalar mu: q_o = kx^2 - mu eps_o of the exact ordinary factor of the quartic
     bool uni = false;
     cx<T> qo = mk<T>(T(0), T(0));
     if constexpr (NM && sizeof(T) == 8) {
@@ -158,16 +150,39 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
         qo = fnma(mu, eo, mk<T>(k * k, T(0)));
       }
     }
-    Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail, uni, qo);
-    if (L.kind == HO_ANISO_EXIT) {
-      substrate_plane(D, s, y0, y1);
-      if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
-    } else if constexpr (FAST != 1) {   // (the fast build has left every crystal film above)
-      const T d = T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)));
-      const cx<T> c = mk<T>(T(0), -(k0 * d));
-      if (STABLE) film_stable<T, NM, FAST, !EXTRAS>(D, s, c, y0, y1, w, bail);
-      else film_transfer<T, NM, FAST, !EXTRAS>(D, s, c, y0, y1, w, bail);
+    // A film is one cubic polynomial in Delta wherever that is accurate; its coefficients come from
+    //  * the pair-symmetric closed form (un-tilted or uniaxial crystal: no spectral split), else
+    //  * the spectral split (thin film: all four mode exponentials within e^6 of each other);
+    // both end in ONE application site.  Thick films keep the invariant-subspace forms.
+    cx<T> a0, a1, a2, a3;
+    cx<T> c = mk<T>(T(0), T(0));
+    bool cubic = false;
+    if (L.kind == HO_ANISO_FILM) {
+      c = mk<T>(T(0), -(k0 * T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)))));   // -i k0 d (reference waves.py:326)
+      if (FAST == 1 || uni || (FAST == 0 && untilted))
+        cubic = pair_symmetric_film_coeffs<T, FAST == 2>(c3, c2, c1, c0, c, uni, qo, a0, a1, a2, a3);
+      if constexpr (FAST == 1) {
+        if (!cubic) { bail = true; return; }
+      }
     }
+    if (!cubic) {
+      Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail, uni, qo);
+      if (L.kind == HO_ANISO_EXIT) {
+        substrate_plane(D, s, y0, y1);
+        if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
+        return;
+      }
+      if constexpr (FAST != 1) {   // (the fast build has left every crystal film above)
+        cubic = film_thin_coeffs<T, !EXTRAS>(s, c, a0, a1, a2, a3);
+        if (!cubic) {
+          if constexpr (FAST != 0) { bail = true; return; }   // thick film: left to the general kernel
+          if (STABLE) film_stable_thick<T, NM>(D, s, c, y0, y1, w);
+          else film_transfer_thick<T, NM>(D, s, c, y0, y1, w);
+          return;
+        }
+      }
+    }
+    film_cubic<T, NM, STABLE>(D, a0, a1, a2, a3, y0, y1, w);
   }
 }
 

@@ -213,8 +213,7 @@ modes_kernel(const __grid_constant__ ho_problem_t P, int layer, ModesOut out, in
           if (iso) {
             iso_film(k, eps, mu, c, false, y0, y1, wm);
           } else {
-            bool bail = false;
-            film_transfer<T, NM, false>(D, s, c, y0, y1, wm, bail);
+            film_transfer<T, NM>(D, s, c, y0, y1, wm);
             // undo the re-basing of a separated forward pair: the matrix wants exp(cD) e_k itself
             if (wm[1].re != 0.0 || wm[1].im != 0.0) y1 = axpy(-wm[1], y0, y1);
             if (wm[2].re != 0.0 || wm[2].im != 0.0) y0 = axpy(-wm[2], y1, y0);
