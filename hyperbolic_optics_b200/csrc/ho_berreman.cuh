@@ -112,23 +112,32 @@ template <typename T> __device__ __forceinline__ Vec4<T> matvec(const Delta<T>& 
   return r;
 }
 
-// det(lambda I - D) = lambda^4 + c3 lambda^3 + c2 lambda^2 + c1 lambda + c0
-template <typename T> __device__ __forceinline__ void charpoly(const Delta<T, true>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
-  cx<T> a2 = D.a * D.a, ab = D.a * D.b;
+// det(lambda I - D) = lambda^4 + c3 lambda^3 + c2 lambda^2 + c1 lambda + c0, in two halves: a uniaxial
+// film only needs c3 and c2 (its quartic factorises), everything else all four
+template <typename T> __device__ __forceinline__ void charpoly_hi(const Delta<T, true>& D, cx<T>& c3, cx<T>& c2) {
   c3 = T(-2) * D.a;
-  c2 = fnma(D.f, D.h, fnma(D.d, D.j, a2));
+  c2 = fnma(D.f, D.h, fnma(D.d, D.j, D.a * D.a));
+}
+template <typename T> __device__ __forceinline__ void charpoly_lo(const Delta<T, true>& D, cx<T>& c1, cx<T>& c0) {
+  cx<T> a2 = D.a * D.a, ab = D.a * D.b;
   c1 = T(2) * (D.f * fnma(D.b, D.g, D.a * D.h));
   c0 = D.f * fma(D.d, fma(D.h, D.j, D.g * D.g), fma(D.b * D.b, D.j, fnma(a2, D.h, T(2) * (ab * D.g))));
 }
-
-template <typename T> __device__ __forceinline__ void charpoly(const Delta<T>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
-  cx<T> a2 = D.a * D.a, e2 = D.e * D.e, cg = D.c * D.g, dj = D.d * D.j, fh = D.f * D.h;
-  cx<T> bcj = D.b * D.c * D.j, bf = D.b * D.f, ae = D.a * D.e;
+template <typename T> __device__ __forceinline__ void charpoly_hi(const Delta<T>& D, cx<T>& c3, cx<T>& c2) {
+  cx<T> a2 = D.a * D.a, e2 = D.e * D.e, cg = D.c * D.g, dj = D.d * D.j, fh = D.f * D.h, ae = D.a * D.e;
   c3 = T(-2) * (D.a + D.e);
   c2 = a2 + T(4) * ae - T(2) * cg - dj + e2 - fh;
+}
+template <typename T> __device__ __forceinline__ void charpoly_lo(const Delta<T>& D, cx<T>& c1, cx<T>& c0) {
+  cx<T> a2 = D.a * D.a, e2 = D.e * D.e, cg = D.c * D.g, dj = D.d * D.j, fh = D.f * D.h;
+  cx<T> bcj = D.b * D.c * D.j, bf = D.b * D.f, ae = D.a * D.e;
   c1 = T(-2) * (a2 * D.e - D.a * cg + D.a * e2 - D.a * fh - bcj + bf * D.g - D.e * cg - D.e * dj);
   c0 = a2 * e2 - a2 * fh + T(2) * (D.a * bf * D.g) - T(2) * (ae * cg) + D.b * bf * D.j - T(2) * (D.e * bcj)
        + cg * cg + D.c * D.c * D.h * D.j - e2 * dj + D.d * D.f * D.g * D.g + dj * fh;
+}
+template <typename T, bool NM> __device__ __forceinline__ void charpoly(const Delta<T, NM>& D, cx<T>& c3, cx<T>& c2, cx<T>& c1, cx<T>& c0) {
+  charpoly_hi(D, c3, c2);
+  charpoly_lo(D, c1, c0);
 }
 
 // Roots of y^2 + bq y + cq without cancellation.  A pair closer than ~sqrt(tau) relative to |bq|
@@ -644,54 +653,52 @@ template <typename T, bool NM> __device__ __forceinline__ void film_transfer_thi
 //   3. the two interpolants are merged into one cubic by the projector formula of cubic_coeffs.
 // Uniaxial film (`uni`, q_o = kx^2 - mu eps_o; any orientation): the two pairs are known in closed
 // form -- the ordinary pair +-mu_o, mu_o^2 = -q_o, and the extraordinary pair delta_e +- mu_e of
-// x^2 + c3 x + q_e, q_e = c2 - q_o -- so steps 1 reduces to a consistency check of that
-// factorisation against the computed quartic (it also guards a wrong hint), and e^{c delta_e} is a
-// true exponential when the crystal is tilted (delta_e = -c3/2 not small).
+// x^2 + c3 x + q_e, q_e = c2 - q_o -- so step 1 disappears (c1 and c0 are not even computed), and
+// e^{c delta_e} is a true exponential when the crystal is tilted (delta_e = -c3/2 not small).
 // Returns false when the point has to take the general path: odd coefficients not small, y0 ~ y1
 // (the merge would lose more than 3 digits: near-normal incidence on a c-cut uniaxial film),
 // polish not converged, or thick film (a |Re(c mu)| >= 3).
-// UNI_ONLY (lean kernel for tilted stacks): only the uniaxial closed form is compiled.
-template <typename T, bool UNI_ONLY = false> __device__ __forceinline__ bool pair_symmetric_film_coeffs(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T> c, bool uni, cx<T> qo,
-                                                                                cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+// Step 1 for a general un-tilted crystal: the two pair factors (as a Spectrum: "f" = pair 0, "b" = pair 1).
+template <typename T> __device__ __forceinline__ bool pair_factors_untilted(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, Spectrum<T>& s) {
   const T odd_tol = sizeof(T) == 8 ? T(1e-12) : T(1e-6);
   const T step_tol = sizeof(T) == 8 ? T(1e-20) : T(1e-9);
-  Spectrum<T> s;
-  if (uni) {
-    const cx<T> qe = c2 - qo;
-    const cx<T> t1 = c3 * qo, t0 = qo * qe;
-    const T fac_tol = T(1e-24);   // |c1 - c3 q_o|, |c0 - q_o q_e| at rounding level
-    uni = norm2(c1 - t1) <= fac_tol * (norm2(t1) + norm2(c1)) && norm2(c0 - t0) <= fac_tol * norm2(t0);
-    s.sf = mk<T>(T(0), T(0)); s.pf = qo; s.sb = -c3; s.pb = qe;
-  }
-  if (!uni) {
-    if constexpr (UNI_ONLY) return false;
-    T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
-    if (!((n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2)))) return false;
-    cx<T> y0, y1;
-    quad_roots(c2, c0, y0, y1);
-    cx<T> dy = y0 - y1;
-    if (!(norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1)))) return false;
-    cx<T> idy = recip(dy);
-    cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
-    // two steps; a third only where the second still moved (rate ~ tilt |mu| / |y0 - y1|: step k has
-    // size rate^k, the error after it rate^(k+1))
-    bool done = false;
+  T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
+  if (!((n3 * n3 <= odd_tol * n2) && (n1 * n1 <= odd_tol * (n2 * n2 * n2)))) return false;
+  cx<T> y0, y1;
+  quad_roots(c2, c0, y0, y1);
+  cx<T> dy = y0 - y1;
+  if (!(norm2(dy) >= T(1e-6) * (norm2(y0) + norm2(y1)))) return false;
+  cx<T> idy = recip(dy);
+  cx<T> u = mk<T>(T(0), T(0)), v = -y0, b1, b0, du, dv;
+  // two steps; a third only where the second still moved (rate ~ tilt |mu| / |y0 - y1|: step k has
+  // size rate^k, the error after it rate^(k+1))
+  bool done = false;
 #pragma unroll 1
-    for (int it = 0; it < 3 && !done; ++it) {
-      b1 = c3 - u;
-      b0 = fnma(u, b1, c2 - v);
-      du = fnma(v, b1, fnma(u, b0, c1)) * idy;
-      dv = fnma(v, b0, c0) * idy;
-      u = u + du;
-      v = v + dv;
-      T nv = norm2(v), ndu = norm2(du);
-      done = it >= 1 && norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv;  // |du|^2 <= tol |v|
-    }
-    if (!done) return false;
+  for (int it = 0; it < 3 && !done; ++it) {
     b1 = c3 - u;
     b0 = fnma(u, b1, c2 - v);
-    s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
+    du = fnma(v, b1, fnma(u, b0, c1)) * idy;
+    dv = fnma(v, b0, c0) * idy;
+    u = u + du;
+    v = v + dv;
+    T nv = norm2(v), ndu = norm2(du);
+    done = it >= 1 && norm2(dv) <= step_tol * nv && ndu * ndu <= step_tol * step_tol * nv;  // |du|^2 <= tol |v|
   }
+  if (!done) return false;
+  b1 = c3 - u;
+  b0 = fnma(u, b1, c2 - v);
+  s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
+  return true;
+}
+// Step 1 for a uniaxial crystal: the ordinary and the extraordinary factor, exact (the host vouches
+// for the hint: plan._ordinary_value checks the rotated table against it).  Only c3 and c2 are needed.
+template <typename T> __device__ __forceinline__ void pair_factors_uniaxial(cx<T> c3, cx<T> c2, cx<T> qo, Spectrum<T>& s) {
+  s.sf = mk<T>(T(0), T(0)); s.pf = qo; s.sb = -c3; s.pb = c2 - qo;
+}
+// Steps 2 and 3.  `exp_delta`: pair 1 may sit off the origin (tilted uniaxial film: delta_e = -c3/2
+// not small), e^{c delta_e} is then a true exponential.
+template <typename T> __device__ __forceinline__ bool pair_symmetric_film_coeffs(const Spectrum<T>& s, cx<T> c, bool exp_delta,
+                                                                                cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
   cx<T> d0 = T(0.5) * s.sf, d1 = T(0.5) * s.sb;   // pair centres delta_i
   const cx<T> cc = c * c;
   cx<T> m0 = fma(d0, d0, -s.pf), m1 = fma(d1, d1, -s.pb);              // mu_i^2
@@ -705,7 +712,7 @@ template <typename T, bool UNI_ONLY = false> __device__ __forceinline__ bool pai
   const cx<T> one = mk<T>(T(1), T(0));
   cx<T> e0 = fma(T(0.5) * x0, x0, one + x0), e1;  // e^{c delta}, |c delta| < 1e-5
   if (norm2(x1) < T(1e-10)) e1 = fma(T(0.5) * x1, x1, one + x1);
-  else if (uni) e1 = cexp(x1);     // tilted uniaxial film
+  else if (exp_delta) e1 = cexp(x1);
   else return false;
   cx<T> h0, h1;
   projector_coeffs(s, h0, h1);

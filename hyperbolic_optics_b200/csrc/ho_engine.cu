@@ -139,7 +139,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     ZRow<T> z;
     Delta<T, NM> D = layer_delta<T, NM>(L, k, f, b, z);
     cx<T> c3, c2, c1, c0;
-    charpoly(D, c3, c2, c1, c0);
+    charpoly_hi(D, c3, c2);
     // uniaxial crystal with scalar mu: q_o = kx^2 - mu eps_o of the exact ordinary factor of the quartic
     bool uni = false;
     cx<T> qo = mk<T>(T(0), T(0));
@@ -156,16 +156,29 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     // both end in ONE application site.  Thick films keep the invariant-subspace forms.
     cx<T> a0, a1, a2, a3;
     cx<T> c = mk<T>(T(0), T(0));
-    bool cubic = false;
+    bool cubic = false, have_lo = false;
     if (L.kind == HO_ANISO_FILM) {
       c = mk<T>(T(0), -(k0 * T(__ldg(L.thickness + (L.n_thickness > 1 ? t : 0)))));   // -i k0 d (reference waves.py:326)
-      if (FAST == 1 || uni || (FAST == 0 && untilted))
-        cubic = pair_symmetric_film_coeffs<T, FAST == 2>(c3, c2, c1, c0, c, uni, qo, a0, a1, a2, a3);
+      Spectrum<T> pairs;
+      bool have_pairs = false;
+      if (uni) {
+        pair_factors_uniaxial(c3, c2, qo, pairs);
+        have_pairs = true;
+      }
+      if constexpr (FAST != 2) {   // (the lean build for tilted stacks only has the uniaxial closed form)
+        if (!uni && (FAST == 1 || untilted)) {
+          charpoly_lo(D, c1, c0);
+          have_lo = true;
+          have_pairs = pair_factors_untilted(c3, c2, c1, c0, pairs);
+        }
+      }
+      if (have_pairs) cubic = pair_symmetric_film_coeffs(pairs, c, uni, a0, a1, a2, a3);
       if constexpr (FAST == 1) {
         if (!cubic) { bail = true; return; }
       }
     }
     if (!cubic) {
+      if (!have_lo) charpoly_lo(D, c1, c0);
       Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail, uni, qo);
       if (L.kind == HO_ANISO_EXIT) {
         substrate_plane(D, s, y0, y1);

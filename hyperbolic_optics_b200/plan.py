@@ -222,7 +222,7 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
                 lp = LayerPlan(KIND_ANISO_EXIT, kind)
             lp.eps, lp.mu, lp.mu_scalar = np.ascontiguousarray(eps), np.ascontiguousarray(mu), mu_scalar
             lp.eps_scalar = eps_scalar
-            lp.eps_ordinary = None if eps_scalar or not mu_scalar else _ordinary_value(eps_packed)
+            lp.eps_ordinary = None if eps_scalar or not mu_scalar else _ordinary_value(eps_packed, lp.eps)
             lp.cos_beta, lp.sin_beta, lp.material = cos_b, sin_b, material
             lp.rotation_xy = np.eye(3) if eps_scalar else q
         elif kind == TYPE_ISO_EXIT:
@@ -252,7 +252,7 @@ def build_plan(scenario: ScenarioSetup, layer_data_list) -> StackPlan:
     return plan
 
 
-def _ordinary_value(eps_packed):
+def _ordinary_value(eps_packed, rotated):
     """``[Fe]`` ordinary principal value when the un-rotated tensor is diagonal with the same two
     equal entries at every frequency (uniaxial crystal: Quartz, Calcite, Sapphire, hBN, or an
     arbitrary diagonal tensor of that shape), else ``None``.  Rotations keep the property, so the
@@ -262,8 +262,22 @@ def _ordinary_value(eps_packed):
     xx, yy, zz = eps_packed[:, 0], eps_packed[:, 3], eps_packed[:, 5]
     for same, value in ((xx == yy, xx), (xx == zz, xx), (yy == zz, yy)):
         if np.all(same):
-            return np.ascontiguousarray(value, dtype=np.complex128)
+            value = np.ascontiguousarray(value, dtype=np.complex128)
+            return value if _is_double_eigenvalue(rotated, value) else None
     return None
+
+
+def _is_double_eigenvalue(rotated, value) -> bool:
+    """The kernels use the hint without checking it per point, so it is checked here once per table:
+    ``eps - eps_o I`` of the ROTATED table must have rank one (all 2x2 minors vanish to rounding)."""
+    m = unpack_symmetric(rotated) - value[:, None, None] * np.eye(3)
+    scale = np.abs(m).max(axis=(1, 2)) ** 2 + 1e-300
+    worst = 0.0
+    for (i, j) in ((0, 1), (0, 2), (1, 2)):
+        for (k, l) in ((0, 1), (0, 2), (1, 2)):
+            minor = m[:, i, k] * m[:, j, l] - m[:, i, l] * m[:, j, k]
+            worst = max(worst, float(np.max(np.abs(minor) / scale)))
+    return worst <= 1e-12
 
 
 def _optically_thin(lp, k0) -> bool:
