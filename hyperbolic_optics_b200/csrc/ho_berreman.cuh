@@ -60,8 +60,8 @@ template <typename T> __device__ __forceinline__ Sym6<T> rotate_z(const Sym6<T>&
 }
 
 // scalar-mu flavour: m = mu * I
-template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k, const Sym6<T>& e, cx<T> mu, ZRow<T>& z) {
-  cx<T> ie = recip(e.zz), im = recip(mu);
+// ie = 1 / eps_zz, im = 1 / mu
+template <typename T> __device__ __forceinline__ Delta<T, true> berreman_nm(T k, const Sym6<T>& e, cx<T> mu, cx<T> ie, cx<T> im, ZRow<T>& z) {
   z.e20 = e.xz; z.e21 = e.yz; z.ie22 = ie; z.m20 = mk<T>(T(0), T(0)); z.m21 = z.m20; z.im22 = im;
   T k2 = k * k;
   Delta<T, true> D;
@@ -245,10 +245,7 @@ template <typename T> __device__ __forceinline__ void classify(const cx<T> lam[4
 // complementary factor lambda^2 + b1 lambda + b0 follows by deflation.  Per-point early exits:
 // the Newton step is skipped once the residual of the division is at rounding level, and the
 // loop ends once a step is negligible (accurate start values need exactly one step).
-// accept_start: the start values may already be exact (uniaxial factorisation): the residual test
-// also applies before the first step.
-template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0,
-                                                              bool accept_start = false) {
+template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, cx<T>& u, cx<T>& v, cx<T>& b1, cx<T>& b0) {
   const T res_tol2 = sizeof(T) == 8 ? T(1e-28) : T(1e-12);
   const T step_tol2 = sizeof(T) == 8 ? T(1e-22) : T(1e-7);
   const int max_steps = 3;
@@ -260,7 +257,7 @@ template <typename T> __device__ __forceinline__ bool bairstow(cx<T> c3, cx<T> c
     cx<T> t1 = u * b0, t2 = v * b1, t3 = v * b0;
     cx<T> r1 = c1 - t1 - t2;
     cx<T> r0 = c0 - t3;
-    if ((it > 0 || accept_start) && norm2(r1) <= res_tol2 * (norm2(t1) + norm2(t2)) && norm2(r0) <= res_tol2 * norm2(t3)) { converged = true; break; }
+    if (it > 0 && norm2(r1) <= res_tol2 * (norm2(t1) + norm2(t2)) && norm2(r0) <= res_tol2 * norm2(t3)) { converged = true; break; }
     if (it == max_steps) break;
     cx<T> umb = u - b1;
     cx<T> j22 = v - b0;
@@ -291,47 +288,30 @@ template <typename T> __device__ __forceinline__ cx<T> forward_sqrt(cx<T> y) {
 }
 
 // charpoly -> start values -> Bairstow polish of the forward quadratic factor.
-// Start values, cheapest first:
-//  * odd coefficients negligible (z is a principal axis of the rotated tensors up to the reference's
-//    hidden 1e-8 angle offsets -- every un-tilted crystal): the quartic is a perturbed biquadratic and
-//    the forward pair comes from three square roots;
-//  * uniaxial crystal (`uni`, any orientation; q_o = kx^2 - mu eps_o from ho_layer_t.eps_ordinary): the
-//    quartic factorises exactly into the ordinary and the extraordinary quadratic,
-//    (x^2 + q_o)(x^2 + c3 x + q_e) with q_e = c2 - q_o: two square roots, then the reference's
-//    forward rule on the four roots;
-//  * otherwise Ferrari / Cardano + the forward rule.
-// A start that fails the convergence check of the polish falls through to the next one.
+// Start values: when the odd coefficients are negligible (z is a principal axis of the rotated
+// tensors up to the reference's hidden 1e-8 angle offsets -- every un-tilted crystal) the quartic
+// is a perturbed biquadratic and the forward pair comes from three square roots; otherwise
+// Ferrari + classification.  A biquadratic start that fails to converge falls back to Ferrari.
 // FAST == 1 (fast-path kernel): only the biquadratic start is compiled; a point that would need
-// more sets `bail` and is finished later by the general kernel.  FAST == 2 (lean kernel for
+// Ferrari sets `bail` and is finished later by the general kernel.  FAST == 2 (lean kernel for
 // tilted stacks): the general start values, as FAST == 0.
-template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail,
-                                                                                    bool uni = false, cx<T> qo = cx<T>{T(0), T(0)}) {
+// (Uniaxial crystals do not come here: split_uniaxial.)
+template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split_spectrum(cx<T> c3, cx<T> c2, cx<T> c1, cx<T> c0, bool& bail) {
   const T tau4 = T(1e-20);
   T n2 = norm2(c2), n3 = norm2(c3), n1 = norm2(c1);
   bool biq = (n3 * n3 <= tau4 * n2) && (n1 * n1 <= tau4 * (n2 * n2 * n2));
   cx<T> u, v, b1, b0;
   if constexpr (FAST == 1) {
-    // (un-tilted plan: a uniaxial crystal keeps the ordinary / extraordinary root pairs +-mu_o and
-    // delta_e +- mu_e, the forward member of each by the reference's rule on the pair -- no ranking)
-    cx<T> y0, y1, m0, m1;
-    if (uni) {
-      m0 = forward_sqrt(-qo);
-      quad_roots(c3, c2 - qo, y0, y1);
-      const bool f0 = (ho_abs(y0.im) > T(1e-9)) ? (y0.im > T(0)) : (y0.re > T(0));
-      const bool f1 = (ho_abs(y1.im) > T(1e-9)) ? (y1.im > T(0)) : (y1.re > T(0));
-      m1 = f0 ? y0 : y1;
-      bail = bail || (f0 == f1);   // not one forward and one backward root: the general kernel ranks all four
-    } else {
-      quad_roots(c2, c0, y0, y1);
-      m0 = forward_sqrt(y0); m1 = forward_sqrt(y1);
-    }
+    cx<T> y0, y1;
+    quad_roots(c2, c0, y0, y1);
+    cx<T> m0 = forward_sqrt(y0), m1 = forward_sqrt(y1);
     u = -(m0 + m1);
     v = m0 * m1;
-    bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0, uni);
-    bail = bail || !(biq || uni) || !ok;
+    bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
+    bail = bail || !biq || !ok;
   } else {
 #pragma unroll 1
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
       if (biq) {
         cx<T> y0, y1;
         quad_roots(c2, c0, y0, y1);
@@ -340,13 +320,7 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
         v = m0 * m1;
       } else {
         cx<T> lam[4];
-        if (uni) {
-          lam[0] = csqrt(-qo);
-          lam[1] = -lam[0];
-          quad_roots(c3, c2 - qo, lam[2], lam[3]);
-        } else {
-          start_roots(c3, c2, c1, c0, lam);
-        }
+        start_roots(c3, c2, c1, c0, lam);
         bool fwd[4];
         classify(lam, fwd);
         cx<T> sf = mk<T>(T(0), T(0)), pf = mk<T>(T(1), T(0));
@@ -357,14 +331,44 @@ template <typename T, int FAST = 0> __device__ __forceinline__ Spectrum<T> split
         u = -sf;
         v = pf;
       }
-      bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0, !biq && uni);
-      if (ok || !(biq || uni)) break;
-      if (biq) biq = false; else uni = false;
+      bool ok = bairstow(c3, c2, c1, c0, u, v, b1, b0);
+      if (ok || !biq) break;
+      biq = false;
     }
   }
   Spectrum<T> s;
   s.sf = -u; s.pf = v; s.sb = -b1; s.pb = b0;
   return s;
+}
+
+// Spectral split of a uniaxial crystal (any orientation; q_o = kx^2 - mu eps_o from
+// ho_layer_t.eps_ordinary): the quartic factorises exactly into the ordinary and the extraordinary
+// quadratic, (x^2 + q_o)(x^2 + c3 x + q_e) with q_e = c2 - q_o, so the four roots are two square
+// roots away -- no Ferrari, no polish, and c1, c0 are not needed at all (the host vouches for the
+// hint: plan._ordinary_value).  Forward pair by the reference's rule (waves.py:273-289) on the four
+// roots; the fast build uses the rule per root and reports a root pair that is not one forward +
+// one backward (`false`: the caller falls back to the general split).
+template <typename T, int FAST = 0> __device__ __forceinline__ bool split_uniaxial(cx<T> c3, cx<T> c2, cx<T> qo, Spectrum<T>& s) {
+  cx<T> lam[4];
+  lam[0] = csqrt(-qo);
+  lam[1] = -lam[0];
+  quad_roots(c3, c2 - qo, lam[2], lam[3]);
+  bool fwd[4];
+  if constexpr (FAST == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fwd[i] = (ho_abs(lam[i].im) > T(1e-9)) ? (lam[i].im > T(0)) : (lam[i].re > T(0));
+    if (fwd[0] == fwd[1] || fwd[2] == fwd[3]) return false;
+  } else {
+    classify(lam, fwd);
+  }
+  const cx<T> one = mk<T>(T(1), T(0)), zero = mk<T>(T(0), T(0));
+  s.sf = zero; s.pf = one; s.sb = zero; s.pb = one;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fwd[i]) { s.sf = s.sf + lam[i]; s.pf = s.pf * lam[i]; }
+    else        { s.sb = s.sb + lam[i]; s.pb = s.pb * lam[i]; }
+  }
+  return true;
 }
 
 // h(x) = h0 + h1 x with h q_b = 1 (mod q_f): the forward spectral projector is q_b(D) h(D)

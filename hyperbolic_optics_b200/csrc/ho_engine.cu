@@ -83,7 +83,15 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
   T cb = T(__ldg(L.cos_beta + bi)), sb = T(__ldg(L.sin_beta + bi));
   Sym6<T> e = rotate_z(load_sym<T>(L.eps, L.n_eps > 1 ? f : 0), cb, sb);
   if constexpr (NM) {
-    return berreman_nm(k, e, ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0)), z);
+    const cx<T> mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
+    cx<T> ie, im;
+    if (L.nm_recip != nullptr) {   // per-frequency reciprocals from the host
+      const ho_c128* rc = L.nm_recip + 2 * (int64_t)((L.n_eps > 1 || L.n_mu > 1) ? f : 0);
+      ie = ldc<T>(rc); im = ldc<T>(rc + 1);
+    } else {
+      ie = recip(e.zz); im = recip(mu);
+    }
+    return berreman_nm(k, e, mu, ie, im, z);
   } else {
     Sym6<T> m = load_sym<T>(L.mu, L.n_mu > 1 ? f : 0);
     if (!L.mu_scalar) m = rotate_z(m, cb, sb);
@@ -178,8 +186,11 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
       }
     }
     if (!cubic) {
-      if (!have_lo) charpoly_lo(D, c1, c0);
-      Spectrum<T> s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail, uni, qo);
+      Spectrum<T> s;
+      if (!(uni && split_uniaxial<T, FAST>(c3, c2, qo, s))) {
+        if (!have_lo) charpoly_lo(D, c1, c0);
+        s = split_spectrum<T, FAST>(c3, c2, c1, c0, bail);
+      }
       if (L.kind == HO_ANISO_EXIT) {
         substrate_plane(D, s, y0, y1);
         if constexpr (EXTRAS) exit_mode_basis(D, s, z, k, y0, y1, binv);
