@@ -32,7 +32,7 @@ class LayerDesc(C.Structure):
         ("cos_beta", C.c_void_p), ("sin_beta", C.c_void_p), ("thickness", C.c_void_p),
         ("iso_eps", c128), ("iso_mu", c128),
         ("exit_cos", C.c_void_p), ("exit_n", C.c_double),
-        ("eps_ordinary", C.c_void_p), ("nm_recip", C.c_void_p),
+        ("eps_ordinary", C.c_void_p),
     ]
 
 

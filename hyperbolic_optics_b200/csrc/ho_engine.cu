@@ -83,15 +83,7 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
   T cb = T(__ldg(L.cos_beta + bi)), sb = T(__ldg(L.sin_beta + bi));
   Sym6<T> e = rotate_z(load_sym<T>(L.eps, L.n_eps > 1 ? f : 0), cb, sb);
   if constexpr (NM) {
-    const cx<T> mu = ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0));
-    cx<T> ie, im;
-    if (L.nm_recip != nullptr) {   // per-frequency reciprocals from the host
-      const ho_c128* rc = L.nm_recip + 2 * (int64_t)((L.n_eps > 1 || L.n_mu > 1) ? f : 0);
-      ie = ldc<T>(rc); im = ldc<T>(rc + 1);
-    } else {
-      ie = recip(e.zz); im = recip(mu);
-    }
-    return berreman_nm(k, e, mu, ie, im, z);
+    return berreman_nm(k, e, ldc<T>(L.mu + 6 * (int64_t)(L.n_mu > 1 ? f : 0)), z);
   } else {
     Sym6<T> m = load_sym<T>(L.mu, L.n_mu > 1 ? f : 0);
     if (!L.mu_scalar) m = rotate_z(m, cb, sb);

@@ -87,10 +87,6 @@ class DeviceProblem:
                                 (i, "cos_beta", self._put_f64(lp.cos_beta)), (i, "sin_beta", self._put_f64(lp.sin_beta))]
                 if lp.eps_ordinary is not None:
                     layer_slots.append((i, "eps_ordinary", self._put_c128(lp.eps_ordinary)))
-                if lp.mu_scalar and not lp.eps_scalar:
-                    with np.errstate(divide="ignore", invalid="ignore"):
-                        recips = np.stack(np.broadcast_arrays(1.0 / lp.eps[:, 5], 1.0 / lp.mu[:, 0]), axis=1)
-                    layer_slots.append((i, "nm_recip", self._put_c128(recips)))
             if lp.thickness is not None:
                 L.n_thickness = lp.thickness.size
                 layer_slots.append((i, "thickness", self._put_f64(lp.thickness)))

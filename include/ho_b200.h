@@ -83,10 +83,6 @@ typedef struct {
      closed form (np.linalg.eig in the reference, waves.py:256-296).  The polish and its convergence
      check are the same; a failed check falls back to the general start values. */
   const ho_c128* eps_ordinary;
-  /* Scalar-mu crystal: (1 / eps_zz, 1 / mu) per frequency, [max(n_eps, n_mu)][2], else NULL (the
-     kernel then takes the two reciprocals per point).  eps_zz is invariant under the z rotation,
-     so both only depend on the frequency (waves.py:221-245 divides by them at every point). */
-  const ho_c128* nm_recip;
 } ho_layer_t;
 
 enum ho_kernel_hint { HO_HINT_NONE = 0, HO_HINT_UNTILTED = 1, HO_HINT_TILTED_THIN = 2 };
