@@ -12,7 +12,7 @@ from pathlib import Path
 
 HO_MAX_LAYERS = 24
 HO_MAX_PEERS = 15
-HO_ABI_VERSION = 14
+HO_ABI_VERSION = 15
 
 HO_ISO_FILM, HO_ANISO_FILM, HO_ANISO_EXIT, HO_ISO_EXIT = 1, 2, 3, 4
 HO_BACKEND_TRANSFER, HO_BACKEND_SCATTERING = 0, 1
@@ -59,6 +59,8 @@ class Outputs(C.Structure):
         ("t_mode", C.c_void_p), ("t_mode_stride", C.c_int64),
         ("power_states", C.c_int32),
         ("n_peers", C.c_int32), ("peer_r", (C.c_void_p * 4) * HO_MAX_PEERS),
+        ("n_rebuild", C.c_int32), ("rebuild_n", C.c_int64 * HO_MAX_PEERS),
+        ("rebuild_r", (C.c_void_p * 4) * HO_MAX_PEERS), ("rebuild_mueller", C.c_void_p * HO_MAX_PEERS),
     ]
 
 

@@ -46,6 +46,11 @@ template <typename T> struct OutPtrs {
   int power_states;  // 2: p, s; 4: + (p + s)/sqrt2, (p + i s)/sqrt2
   int n_peers;       // fused all-gather: further destinations of r_ij (peer memory over NVLink)
   ho::cx<T>* peer[HO_MAX_PEERS][4];
+  // receiving half of the fused all-gather: ranges of r_ij that already arrived, Mueller rebuilt here
+  int n_rebuild;
+  int64_t rebuild_n[HO_MAX_PEERS];
+  const ho::cx<T>* rebuild_r[HO_MAX_PEERS][4];
+  T* rebuild_mueller[HO_MAX_PEERS];
 };
 
 template <typename T> __device__ __forceinline__ ho::cx<T> ldc(const ho_c128* p) {
@@ -340,6 +345,41 @@ template <> __device__ __forceinline__ bool is_sentinel<float>(const ho::cx<floa
 
 enum { MODE_ALL = 0, MODE_FIXUP = 1 };
 
+// Receiving half of the fused all-gather (ho_outputs_t.rebuild_*): element i of every range of
+// reflection coefficients that the peers pushed into this GPU's planes during the previous launch
+// -> its Mueller matrix.  Runs at the top of a point's iteration, before the point's own state is
+// live (no register pressure); the next iteration's operands are prefetched into L2 one iteration
+// (microseconds) ahead, so the loads here do not wait on HBM.
+template <typename T> __device__ __forceinline__ void rebuild_received(const OutPtrs<T>& out, int64_t i, int64_t stride) {
+  using namespace ho;
+#pragma unroll 1
+  for (int p = 0; p < out.n_rebuild; ++p) {
+    const int64_t n = out.rebuild_n[p];
+    if (i + stride < n) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(out.rebuild_r[p][k] + i + stride));
+    }
+    if (i < n) {
+      cx<T> j[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (sizeof(T) == 8) { const double2 v = __ldcs(reinterpret_cast<const double2*>(out.rebuild_r[p][k] + i)); j[k] = mk<T>(v.x, v.y); }
+        else { const float2 v = __ldcs(reinterpret_cast<const float2*>(out.rebuild_r[p][k] + i)); j[k] = mk<T>(v.x, v.y); }
+      }
+      T M[16];
+      mueller_from_jones(j[0], j[1], j[2], j[3], M);
+      T* m = out.rebuild_mueller[p] + 16 * i;
+      if constexpr (sizeof(T) == 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) __stcs(reinterpret_cast<double2*>(m) + q, make_double2(M[2 * q], M[2 * q + 1]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<float4*>(m) + q, make_float4(M[4 * q], M[4 * q + 1], M[4 * q + 2], M[4 * q + 3]));
+      }
+    }
+  }
+}
+
 // NM: every crystal layer of the stack has mu proportional to the identity (all built-in
 // materials) -> sparser Berreman matrix; the general kernel handles full mu tensors.
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
@@ -359,6 +399,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     if (deferred <= cap) { total = deferred; listed = true; }
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    if (out.n_rebuild > 0 && mode == MODE_ALL) rebuild_received(out, i, stride);
     int64_t rel = i;
     if (mode == MODE_FIXUP) {
       if (listed) rel = work[1 + i];
@@ -789,6 +830,20 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
       if (!out->peer_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "peer_r: NULL destination");
       o.peer[p][k] = reinterpret_cast<ho::cx<double>*>(out->peer_r[p][k]);
     }
+  if (out->n_rebuild < 0 || out->n_rebuild > HO_MAX_PEERS) return fail(HO_ERR_BAD_ARGUMENT, "n_rebuild must be 0 .. HO_MAX_PEERS");
+  o.n_rebuild = out->n_rebuild;
+  for (int p = 0; p < o.n_rebuild; ++p) {
+    if (out->rebuild_n[p] < 0 || out->rebuild_n[p] > n_end - n_begin)
+      return fail(HO_ERR_BAD_ARGUMENT, "rebuild_n must be 0 .. n_end - n_begin (thread i of the launch handles element i)");
+    if (!out->rebuild_mueller[p]) return fail(HO_ERR_BAD_ARGUMENT, "rebuild_mueller: NULL destination");
+    o.rebuild_n[p] = out->rebuild_n[p];
+    o.rebuild_mueller[p] = out->rebuild_mueller[p];
+    for (int k = 0; k < 4; ++k) {
+      if (!out->rebuild_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "rebuild_r: NULL source");
+      o.rebuild_r[p][k] = reinterpret_cast<const ho::cx<double>*>(out->rebuild_r[p][k]);
+    }
+  }
+  if (o.n_rebuild > 0 && problem->T > 1) return fail(HO_ERR_BAD_ARGUMENT, "rebuild ranges are not supported on a thickness sweep");
   DeviceScope scope(problem->kx);
   if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;
@@ -815,6 +870,7 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.t_mode_stride = 0;
   o.power_states = 2;
   o.n_peers = 0;
+  o.n_rebuild = 0;
   DeviceScope scope(problem->kx);
   if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;

@@ -227,14 +227,17 @@ class DeviceOutputs:
         return total
 
 
-def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None, select="all", peers=()):
+def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, stream=None, select="all", peers=(), rebuild=()):
     """Launch the fused kernel for points ``[n_begin, n_end)`` into ``out`` (asynchronous).
 
     ``select``: "all" fills every buffer ``out`` holds; "mueller" only the Mueller matrix (and the
     Stokes vector); "power" only the power planes, "no-power" everything else (used to take the power bookkeeping from the stable recursion
     while r_ij / t_ij keep transfer-matrix semantics).  ``peers``: fused all-gather -- per peer GPU the
     four device addresses (pp, ps, sp, ss planes, element 0 of this range) in that GPU's result
-    buffer, mapped into this process; the kernel stores r_ij there too (``ho_outputs_t.peer_r``)."""
+    buffer, mapped into this process; the kernel stores r_ij there too (``ho_outputs_t.peer_r``).
+    ``rebuild``: the receiving half, fused into the same launch -- ``(r_rows, mueller)`` pairs, ``r_rows`` a
+    ``[4, n]`` view of coefficients that already arrived (``n <= n_end - n_begin``), ``mueller`` the
+    contiguous ``[n, 4, 4]`` slice to fill from them (``ho_outputs_t.rebuild_*``)."""
     n_end = problem.n_points if n_end is None else n_end
     if n_end - n_begin > out.n:
         raise ValueError("output buffers are smaller than the requested point range")
@@ -264,6 +267,14 @@ def reflect(problem: DeviceProblem, out: DeviceOutputs, n_begin=0, n_end=None, s
         for p, quad in enumerate(peers):
             for k in range(4):
                 o.peer_r[p][k] = int(quad[k])
+        if len(rebuild) > nat.HO_MAX_PEERS:
+            raise ValueError(f"at most {nat.HO_MAX_PEERS} rebuild ranges")
+        o.n_rebuild = len(rebuild)
+        for p, (rows, mueller) in enumerate(rebuild):
+            o.rebuild_n[p] = int(rows.shape[1])
+            o.rebuild_mueller[p] = mueller.data_ptr()
+            for k in range(4):
+                o.rebuild_r[p][k] = rows[k].data_ptr()
         nat.check(lib.ho_reflect(C.byref(problem.desc), C.byref(o), n_begin, n_end, handle))
     else:
         o = nat.OutputsF32()

@@ -111,21 +111,24 @@ class GatheredSweep:
 
     ``transport="fused"`` (default when symmetric memory is available): the result buffers live in
     symmetric memory (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into
-    every process over NVSwitch) and the reflection kernel itself performs the all-gather -- besides
-    its local planes it stores each r_ij into the peers' buffers (``ho_outputs_t.peer_r``), so the
-    NVLink transfer overlaps the arithmetic point by point inside ONE kernel, with no separate
-    communication kernels competing for SMs.  The step is bound by NVLink ingest
-    (64 B x the points of the other ranks per GPU at <= 900 GB/s), i.e. max(compute, exchange).
+    every process over NVSwitch) and the reflection kernel itself performs the all-gather, both
+    halves of it.  Sending: besides its local planes it stores each r_ij into the peers' buffers
+    (``ho_outputs_t.peer_r``), so the NVLink transfer overlaps the arithmetic point by point inside
+    ONE kernel, with no separate communication kernels competing for SMs.  Receiving: the launch of
+    chunk c also turns the r_ij that the peers pushed during chunk c - 1 into their Mueller
+    matrices (``ho_outputs_t.rebuild_*``: thread i handles element i of every received range), so
+    the HBM-bound rebuild rides in the load/store slots of the FP64-bound arithmetic; only the last
+    chunk's rebuild is a separate epilogue launch.  The step is bound by NVLink ingest
+    (64 B x the points of the other ranks per GPU at <= 900 GB/s) once N >= 4.
     ``transport="dma"``: same symmetric buffers, but each computed chunk is PUSHED into the peers'
     buffers by the copy engines (``cudaMemcpyAsync`` peer-to-peer, one stream per peer) while the
-    next chunk computes -- no SM takes part in the transfer, which leaves them free for the Mueller
-    rebuild of the chunks that have already arrived; the choice for NVLink-bound steps (N >= 4).
+    next chunk computes, and the Mueller planes of received chunks are rebuilt by ``ho_polarimetry``
+    on a side stream.
     ``transport="p2p"``: chunks are exchanged by grouped ``ncclSend`` / ``ncclRecv`` on a second
     stream behind the next chunk's compute (also what the gloo CPU test exercises).
 
     Either way the Mueller planes (128 of the 192 B per point) are NOT sent: they are a pure
-    function of r_ij and HBM is 7x faster than an NVLink port, so each rank rebuilds them for the
-    chunks it received with one ``ho_polarimetry`` pass on a side stream, behind the next chunk."""
+    function of r_ij and HBM is 7x faster than an NVLink port."""
 
     def __init__(self, plan, backend, device, world_size, rank, n_chunks=None, mueller=True, group=None, transport="auto",
                  ctas_per_sm=None):
@@ -144,7 +147,7 @@ class GatheredSweep:
         # is free for the Mueller rebuild on the side stream (measured at N = 8: 11.1 ms at full
         # residency, 11.3 with 1 CTA per SM -- too few stores in flight --, 10.4 with 2).
         if ctas_per_sm is None:
-            ctas_per_sm = 2 if (world_size >= 4 and mueller) else 0
+            ctas_per_sm = 2 if (world_size >= 4 and mueller and transport not in ("auto", "fused")) else 0
         self.problem = engine.DeviceProblem(plan, backend, device, max_launch_points=longest,
                                             protocol="fast" if plan.kernel_hint else "auto", max_ctas_per_sm=ctas_per_sm)
         dev = self.problem.device
@@ -201,16 +204,35 @@ class GatheredSweep:
             # nobody may still be reading the previous step's planes when peers start overwriting them
             with torch.cuda.stream(compute):
                 self._hdl.barrier(channel=0)
+        others = [src for src in range(self.world) if src != self.rank]
+        pending = []   # fused transport: (a, b) ranges of received r_ij whose Mueller planes are still to build
         for c in range(self.n_chunks):
             lo, hi = chunk_range(*self.ranges[self.rank], c, self.n_chunks)
+            # Fused transport: the launch of chunk c is also the RECEIVING half for chunk c - 1 -- thread i
+            # rebuilds the Mueller matrix of element i of every range the peers pushed during the previous
+            # launch (ho_outputs_t.rebuild_*), inside the same kernel: the HBM-bound rebuild shares the
+            # SMs with the FP64-bound arithmetic instead of queueing behind it as a second kernel.
+            rebuild, leftover = [], []
+            if fused and self.mueller is not None:
+                for a, b in pending:
+                    m = min(b, a + max(0, hi - lo))
+                    if m > a:
+                        rebuild.append((self.r[:, a:m], self.mueller[a:m]))
+                    if b > m:
+                        leftover.append((m, b))
+                pending = []
             if hi > lo:
                 view = engine.DeviceOutputs.view(self.r[:, lo:hi], None if self.mueller is None else self.mueller[lo:hi])
-                engine.reflect(self.problem, view, lo, hi, stream=compute, peers=self._peers(lo) if fused else ())
+                engine.reflect(self.problem, view, lo, hi, stream=compute, peers=self._peers(lo) if fused else (), rebuild=rebuild)
+            for a, b in leftover:   # (a peer's chunk longer than ours: the tail goes through the epilogue kernel)
+                polarimetry.mueller_into([self.r[i, a:b] for i in range(4)], self.mueller[a:b], stream=compute)
             arrived = torch.cuda.Event()
             if fused:
                 with torch.cuda.stream(compute):
                     self._hdl.barrier(channel=1 + c % 7)     # every rank's chunk c has landed everywhere
-                arrived.record(compute)
+                if self.mueller is not None:
+                    pending = [r for r in (chunk_range(*self.ranges[src], c, self.n_chunks) for src in others) if r[1] > r[0]]
+                continue
             elif dma:
                 done = torch.cuda.Event()
                 done.record(compute)
@@ -233,12 +255,13 @@ class GatheredSweep:
                 arrived.record(self.side)
             if self.mueller is not None:
                 self.side.wait_event(arrived)
-                for src in range(self.world):
-                    if src == self.rank:
-                        continue
+                for src in others:
                     a, b = chunk_range(*self.ranges[src], c, self.n_chunks)
                     if b > a:
                         polarimetry.mueller_into([self.r[i, a:b] for i in range(4)], self.mueller[a:b], stream=self.side)
             else:
                 compute.wait_event(arrived)
+        # fused transport: the last chunk of every peer has no later launch to ride on
+        for a, b in pending:
+            polarimetry.mueller_into([self.r[i, a:b] for i in range(4)], self.mueller[a:b], stream=compute)
         compute.wait_stream(self.side)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HO_ABI_VERSION 14
+#define HO_ABI_VERSION 15
 #define HO_MAX_LAYERS 24
 #define HO_MAX_PEERS 15
 
@@ -181,6 +181,17 @@ typedef struct {
      HBM is 7x faster than an NVLink port -- the receiver rebuilds them with ho_polarimetry.) */
   int32_t n_peers;
   ho_c128* peer_r[HO_MAX_PEERS][4]; /* [peer][pp, ps, sp, ss] */
+  /* The receiving half of that all-gather, fused into the same kernel: n_rebuild further ranges of
+     reflection coefficients that ALREADY lie in this GPU's planes (a chunk every peer pushed during
+     the previous launch) are turned into their Mueller matrices while this launch computes its own
+     points -- thread i of the launch also handles element i of every range, so the HBM-bound
+     rebuild (64 B read, 128 B written, ~60 flops) rides in the load/store slots of the FP64-bound
+     arithmetic instead of competing with it as a second kernel.  rebuild_n[k] <= n_end - n_begin;
+     rebuild_r[k][j] = element 0 of plane j of range k, rebuild_mueller[k] = its [n][16] output. */
+  int32_t n_rebuild;
+  int64_t rebuild_n[HO_MAX_PEERS];
+  const ho_c128* rebuild_r[HO_MAX_PEERS][4];
+  double* rebuild_mueller[HO_MAX_PEERS];
 } ho_outputs_t;
 
 /* Replaces Structure.execute()'s numerical body (get_layers .. calculate_reflectivity /

@@ -168,7 +168,8 @@ def test_struct_layout_matches_header(tmp_path):
         'printf("%zu %zu %zu\\n", sizeof(ho_material_t), offsetof(ho_material_t, amp), offsetof(ho_material_t, rot)); '
         'printf("%zu %zu %zu\\n", offsetof(ho_problem_t, work), offsetof(ho_problem_t, work_capacity), offsetof(ho_problem_t, kx)); '
         'printf("%zu %zu %zu\\n", sizeof(ho_layer_modes_t), offsetof(ho_layer_modes_t, mA), offsetof(ho_layer_modes_t, pF)); '
-        'printf("%zu %zu\\n", offsetof(ho_outputs_t, n_peers), offsetof(ho_outputs_t, peer_r)); '
+        'printf("%zu %zu %zu %zu\\n", offsetof(ho_outputs_t, n_peers), offsetof(ho_outputs_t, peer_r), '
+        'offsetof(ho_outputs_t, rebuild_n), offsetof(ho_outputs_t, rebuild_mueller)); '
         'return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(probe), "-o", str(exe)], check=True)
@@ -179,7 +180,8 @@ def test_struct_layout_matches_header(tmp_path):
                    nat.Polarimetry.mueller.offset, ctypes.sizeof(nat.MaterialDesc), nat.MaterialDesc.amp.offset,
                    nat.MaterialDesc.rot.offset, nat.Problem.work.offset, nat.Problem.work_capacity.offset, nat.Problem.kx.offset,
                    ctypes.sizeof(nat.LayerModes), nat.LayerModes.mA.offset, nat.LayerModes.pF.offset,
-                   nat.Outputs.n_peers.offset, nat.Outputs.peer_r.offset]
+                   nat.Outputs.n_peers.offset, nat.Outputs.peer_r.offset, nat.Outputs.rebuild_n.offset,
+                   nat.Outputs.rebuild_mueller.offset]
 
 
 def test_product_never_imports_oracle():
