@@ -382,7 +382,7 @@ def run_b200_arm(args, rank, local_rank, world):
     gathered = None
     if world > 1 and not args.no_gather:
         sweep = sharding.GatheredSweep(plan, "transfer", device, world, rank, n_chunks=args.gather_chunks, mueller=not args.gather_no_mueller,
-                                       transport=args.gather_transport, ctas_per_sm=args.gather_ctas_per_sm)
+                                       transport=args.gather_transport, ctas_per_sm=args.gather_ctas_per_sm, graph=not args.gather_no_graph)
         g_ms, _ = timed(lambda: sweep.run(stream), args.steps, args.warmup)
         # correctness of the gathered result: every rank checks a foreign slab against a direct evaluation
         peer = (rank + 1) % world
@@ -399,15 +399,17 @@ def run_b200_arm(args, rank, local_rank, world):
         gathered = {
             "value": n_total / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms, "chunks": sweep.n_chunks,
             "transport": sweep.transport, "transport_error": sweep.transport_error,
-            "what": ("all-gather FUSED into the reflection kernel: every r_ij (64 B/point) is also stored into the peers' result "
-                     "buffers (symmetric memory over NVSwitch), overlapping the arithmetic inside one kernel"
+            "cuda_graph": sweep._graph is not None, "cuda_graph_error": sweep.graph_error,
+            "what": ("all-gather FUSED into the reflection kernel, both halves: every r_ij (64 B/point) is also stored into the "
+                     "peers' result buffers (symmetric memory over NVSwitch), and the same launch rebuilds the Mueller matrices "
+                     "of the r_ij the peers pushed during the previous chunk"
                      if sweep.transport == "fused" else
                      "all-gather by the copy engines: each computed chunk of the r_ij planes (64 B/point) is pushed into the peers' "
                      "result buffers (symmetric memory over NVSwitch, one stream per peer) behind the next chunk's compute"
                      if sweep.transport == "dma" else
                      "all-gather of the four r_ij planes (64 B/point) by grouped ncclSend/ncclRecv, chunk-pipelined behind "
                      "compute on a second stream") +
-                    "; the Mueller planes (128 B/point) are rebuilt on every rank from the received r_ij by ho_polarimetry "
+                    "; the Mueller planes (128 B/point) are rebuilt on every rank from the received r_ij "
                     "(HBM is 7x an NVLink port) instead of being sent",
             "received_bytes_per_rank": recv, "GBps_received_per_rank": recv / (g_ms * 1e-3) / 1e9,
             "limiter": f"NVLink ingest per GPU: {recv / 1e9:.2f} GB per step at <= 900 GB/s is >= {recv / 900e9 * 1e3:.2f} ms; "
@@ -559,6 +561,7 @@ def main():
     ap.add_argument("--gather-chunks", type=int, default=None)
     ap.add_argument("--gather-transport", default="auto", choices=["auto", "fused", "dma", "p2p"])
     ap.add_argument("--gather-ctas-per-sm", type=int, default=None)
+    ap.add_argument("--gather-no-graph", action="store_true", help="diagnostic: enqueue every gathered step from the host instead of replaying a CUDA graph")
     ap.add_argument("--gather-no-mueller", action="store_true", help="diagnostic: gather r_ij only, do not rebuild the Mueller planes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the gathered strong-scaling measurement at N > 1")

@@ -44,10 +44,16 @@ template <typename T> struct OutPtrs {
   ho::cx<T>* t_pp; ho::cx<T>* t_ps; ho::cx<T>* t_sp; ho::cx<T>* t_ss;
   T* t_mode; int64_t t_mode_stride;
   int power_states;  // 2: p, s; 4: + (p + s)/sqrt2, (p + i s)/sqrt2
-  int n_peers;       // fused all-gather: further destinations of r_ij (peer memory over NVLink)
+};
+
+// Fused all-gather (ho_outputs_t.peer_r, rebuild_*): a separate kernel parameter that only the GATHER
+// instantiations of the reflection kernel carry -- the plain kernels neither see the 1.2 KB of
+// pointers nor compile the code (measured: 2-4 % on C1 / C4 when they did).
+template <typename T, bool ON> struct Gather { int unused; };
+template <typename T> struct Gather<T, true> {
+  int n_peers;       // sending half: further destinations of r_ij (peer memory over NVLink)
   ho::cx<T>* peer[HO_MAX_PEERS][4];
-  // receiving half of the fused all-gather: ranges of r_ij that already arrived, Mueller rebuilt here
-  int n_rebuild;
+  int n_rebuild;     // receiving half: ranges of r_ij that already arrived, Mueller rebuilt here
   int64_t rebuild_n[HO_MAX_PEERS];
   const ho::cx<T>* rebuild_r[HO_MAX_PEERS][4];
   T* rebuild_mueller[HO_MAX_PEERS];
@@ -277,11 +283,11 @@ __device__ __forceinline__ void emit_power(const ho_problem_t& P, const OutPtrs<
 }
 
 // r_ij, Mueller, Stokes (+ power) of one point from its top plane; stores at output offset o
-template <typename T, bool STABLE, bool POWER>
+template <typename T, bool STABLE, bool POWER, bool GATHER = false>
 __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<T>& out, int64_t o, int a,
                                            const ho::Vec4<T>& y0, const ho::Vec4<T>& y1,
                                            const T (*hf)[4], const ho::cx<T> (*wm)[4], int n_upper, const T* lower,
-                                           const ho::cx<T>* binv) {
+                                           const ho::cx<T>* binv, const Gather<T, GATHER>* gather = nullptr) {
   using namespace ho;
   cx<T> r_pp, r_ps, r_sp, r_ss;
   reflect_from_plane(y0, y1, T(__ldg(P.prism_inv_cos + a)), T(__ldg(P.prism_inv_ncos + a)), T(P.prism_inv_n),
@@ -294,12 +300,14 @@ __device__ __forceinline__ void emit_point(const ho_problem_t& P, const OutPtrs<
   if (out.r_ss) st_stream(out.r_ss + o, r_ss);
   // fused all-gather: the same four coefficients into every peer's result buffer (NVLink stores,
   // 512 contiguous bytes per warp and plane), overlapping the next point's arithmetic
+  if constexpr (GATHER) {
 #pragma unroll 1
-  for (int p = 0; p < out.n_peers; ++p) {
-    st_stream(out.peer[p][0] + o, r_pp);
-    st_stream(out.peer[p][1] + o, r_ps);
-    st_stream(out.peer[p][2] + o, r_sp);
-    st_stream(out.peer[p][3] + o, r_ss);
+    for (int p = 0; p < gather->n_peers; ++p) {
+      st_stream(gather->peer[p][0] + o, r_pp);
+      st_stream(gather->peer[p][1] + o, r_ps);
+      st_stream(gather->peer[p][2] + o, r_sp);
+      st_stream(gather->peer[p][3] + o, r_ss);
+    }
   }
   if (out.mueller || out.stokes) {
     T M[16];
@@ -350,7 +358,7 @@ enum { MODE_ALL = 0, MODE_FIXUP = 1 };
 // -> its Mueller matrix.  Runs at the top of a point's iteration, before the point's own state is
 // live (no register pressure); the next iteration's operands are prefetched into L2 one iteration
 // (microseconds) ahead, so the loads here do not wait on HBM.
-template <typename T> __device__ __forceinline__ void rebuild_received(const OutPtrs<T>& out, int64_t i, int64_t stride) {
+template <typename T> __device__ __forceinline__ void rebuild_received(const Gather<T, true>& out, int64_t i, int64_t stride) {
   using namespace ho;
 #pragma unroll 1
   for (int p = 0; p < out.n_rebuild; ++p) {
@@ -385,10 +393,10 @@ template <typename T> __device__ __forceinline__ void rebuild_received(const Out
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
 // FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only the deferred points.
 // work[0] = number of deferred points, work[1 .. cap] = their indices relative to n_begin.
-template <typename T, bool STABLE, bool NM, bool POWER, int FAST>
+template <typename T, bool STABLE, bool NM, bool POWER, int FAST, bool GATHER = false>
 __global__ void __launch_bounds__(kThreads, FAST ? HO_FAST_BLOCKS : HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
-               unsigned* work, unsigned cap) {
+               unsigned* work, unsigned cap, const __grid_constant__ Gather<T, GATHER> gather) {
   using namespace ho;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool small = n_end <= (int64_t)0x7fffffff;
@@ -399,7 +407,9 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     if (deferred <= cap) { total = deferred; listed = true; }
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    if (out.n_rebuild > 0 && mode == MODE_ALL) rebuild_received(out, i, stride);
+    if constexpr (GATHER) {
+      if (mode == MODE_ALL) rebuild_received(gather, i, stride);
+    }
     int64_t rel = i;
     if (mode == MODE_FIXUP) {
       if (listed) rel = work[1 + i];
@@ -456,7 +466,7 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
         continue;
       }
     }
-    emit_point<T, STABLE, POWER>(P, out, rel, a, y0, y1, hf, wm, P.n_layers, nullptr, binv);
+    emit_point<T, STABLE, POWER, GATHER>(P, out, rel, a, y0, y1, hf, wm, P.n_layers, nullptr, binv, &gather);
   }
 }
 
@@ -706,15 +716,29 @@ int grid_for(int64_t n, const void* kernel, int max_ctas_per_sm = 0) {
   return (int)(want < cap ? want : cap);
 }
 
-// Thickness-axis launch: groups per warp as large as possible (reuse) while still leaving
-// enough warps to fill the device; ho_problem_t.tsweep_groups overrides the choice.
+// Thickness-axis launch; ho_problem_t.tsweep_groups overrides the choice of groups per warp.
 template <bool STABLE, bool NM, bool POWER>
 int launch_tsweep(const ho_problem_t* p, const OutPtrs<double>& out, int64_t n_begin, int64_t n_end, int swept,
                   cudaStream_t stream) {
   const int sms = launch_limits((const void*)tsweep_kernel<STABLE, NM, POWER>, kSweepThreads, 0).sms;
   const int64_t groups = (n_end - 1) / p->T - n_begin / p->T + 1;
+  // Groups per warp from a two-term cost model, fitted on BASELINE C5 at its own size (64 x 90 groups x
+  // 80 thicknesses: 0.24 -> 0.19 ms against the former "keep 16 warps per SM" rule) and on the scaled
+  // sweep (147600 groups x 256): a warp executes the t-independent sub-stack once (pass 0, only gpw of
+  // its 32 lanes active) plus ceil(gpw T / 32) full passes over the swept layer and everything above
+  // it; warps beyond one per scheduler queue up.  The largest gpw within 2 % of the minimum wins.
   int gpw = 32;
-  while (gpw > 1 && groups / gpw < (int64_t)sms * 16) gpw >>= 1;
+  {
+    const double lower = 2.0 * (p->n_layers - 1 - swept), upper = swept + 2.0;
+    double best = 0.0;
+    for (int g = 32; g >= 1; g >>= 1) {
+      const double passes = (double)(((int64_t)g * p->T + 31) / 32);
+      const double warps = (double)((groups + g - 1) / g);
+      const double queue = warps / (4.0 * sms);
+      const double cost = (lower + passes * upper) * (queue > 1.0 ? queue : 1.0);
+      if (g == 32 || cost < 0.98 * best) { best = cost; gpw = g; }
+    }
+  }
   if (p->tsweep_groups >= 1 && p->tsweep_groups <= 32) gpw = p->tsweep_groups;
   int row = 16 + (POWER ? 4 * (p->n_layers - 1 - swept) + (out.t_pp ? 8 : 0) : 0);
   row |= 1;  // odd row length: lane <-> row accesses in pass 0 are bank-conflict free
@@ -731,16 +755,16 @@ int launch_tsweep(const ho_problem_t* p, const OutPtrs<double>& out, int64_t n_b
   return 0;
 }
 
-template <typename T, bool STABLE, bool NM, bool POWER>
-int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
-  if constexpr (sizeof(T) == 8) {
+template <typename T, bool STABLE, bool NM, bool POWER, bool GATHER>
+int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, const Gather<T, GATHER>& gather, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
+  if constexpr (sizeof(T) == 8 && !GATHER) {
     int swept = -1;
     for (int l = 0; l < p->n_layers; ++l)
       if (p->layers[l].n_thickness > 1) swept = l;
     if (p->T > 1 && swept >= 0 && p->tsweep_groups >= 0)
       return launch_tsweep<STABLE, NM, POWER>(p, out, n_begin, n_end, swept, stream);
   }
-  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, 0>;
+  const void* kern = (const void*)reflect_kernel<T, STABLE, NM, POWER, 0, GATHER>;
   const int grid = grid_for(n_end - n_begin, kern, p->max_ctas_per_sm);
   if constexpr (sizeof(T) == 8 && !POWER) {
     // (below ~4M points the second launch costs more than the leaner kernel saves)
@@ -753,37 +777,39 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int6
       if (cudaMemsetAsync(p->work, 0, sizeof(unsigned), stream) != cudaSuccess)
         return fail(HO_ERR_CUDA, "work list reset failed: %s", cudaGetErrorString(cudaGetLastError()));
       if (p->hint_fast_path == HO_HINT_TILTED_THIN) {   // lean build: general start values, thin films only
-        const void* lean = (const void*)reflect_kernel<T, STABLE, NM, false, 2>;
-        reflect_kernel<T, STABLE, NM, false, 2><<<grid_for(n, lean, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
+        const void* lean = (const void*)reflect_kernel<T, STABLE, NM, false, 2, GATHER>;
+        reflect_kernel<T, STABLE, NM, false, 2, GATHER><<<grid_for(n, lean, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
       } else {                                          // fast build: un-tilted crystals
-        const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, 1>;
-        reflect_kernel<T, STABLE, NM, false, 1><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap);
+        const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, 1, GATHER>;
+        reflect_kernel<T, STABLE, NM, false, 1, GATHER><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
       }
-      reflect_kernel<T, STABLE, NM, false, 0><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, p->work, (unsigned)cap);
+      // (the fix-up pass also pushes the points it finishes to the peers; the rebuild ran in the first launch)
+      reflect_kernel<T, STABLE, NM, false, 0, GATHER><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_FIXUP, p->work, (unsigned)cap, gather);
       g_launches.fetch_add(1);
       return 0;
     }
   }
-  reflect_kernel<T, STABLE, NM, POWER, 0><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr, 0u);
+  reflect_kernel<T, STABLE, NM, POWER, 0, GATHER><<<grid, kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, nullptr, 0u, gather);
   return 0;
 }
 
 template <typename T, bool STABLE, bool NM>
-int launch_nm(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
+int launch_nm(const ho_problem_t* p, const OutPtrs<T>& out, const Gather<T, true>* gather, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
   if constexpr (sizeof(T) == 8) {
-    if (out.power || out.t_pp) return launch_k<T, STABLE, NM, true>(p, out, n_begin, n_end, stream);
+    if (gather) return launch_k<T, STABLE, NM, false, true>(p, out, *gather, n_begin, n_end, stream);   // (no power / t_* outputs: checked by the caller)
+    if (out.power || out.t_pp) return launch_k<T, STABLE, NM, true, false>(p, out, Gather<T, false>{0}, n_begin, n_end, stream);
   }
-  return launch_k<T, STABLE, NM, false>(p, out, n_begin, n_end, stream);
+  return launch_k<T, STABLE, NM, false, false>(p, out, Gather<T, false>{0}, n_begin, n_end, stream);
 }
 
 template <typename T, bool STABLE>
-int launch(const ho_problem_t* p, const OutPtrs<T>& out, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
+int launch(const ho_problem_t* p, const OutPtrs<T>& out, const Gather<T, true>* gather, int64_t n_begin, int64_t n_end, cudaStream_t stream) {
   if (n_end == n_begin) return HO_OK;
   bool nm = true;
   for (int l = 0; l < p->n_layers; ++l)
     if ((p->layers[l].kind == HO_ANISO_FILM || p->layers[l].kind == HO_ANISO_EXIT) && !p->layers[l].mu_scalar) nm = false;
-  const int rc = nm ? launch_nm<T, STABLE, true>(p, out, n_begin, n_end, stream)
-                    : launch_nm<T, STABLE, false>(p, out, n_begin, n_end, stream);
+  const int rc = nm ? launch_nm<T, STABLE, true>(p, out, gather, n_begin, n_end, stream)
+                    : launch_nm<T, STABLE, false>(p, out, gather, n_begin, n_end, stream);
   if (rc) return rc;
   g_launches.fetch_add(1);
   cudaError_t err = cudaGetLastError();
@@ -824,31 +850,36 @@ int ho_reflect(const ho_problem_t* problem, const ho_outputs_t* out, int64_t n_b
   if (o.t_mode && o.t_mode_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "t_mode_stride is smaller than the point range");
   if (o.power && o.power_stride < n_end - n_begin) return fail(HO_ERR_BAD_ARGUMENT, "power_stride is smaller than the point range");
   if (out->n_peers < 0 || out->n_peers > HO_MAX_PEERS) return fail(HO_ERR_BAD_ARGUMENT, "n_peers must be 0 .. HO_MAX_PEERS");
-  o.n_peers = out->n_peers;
-  for (int p = 0; p < o.n_peers; ++p)
-    for (int k = 0; k < 4; ++k) {
-      if (!out->peer_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "peer_r: NULL destination");
-      o.peer[p][k] = reinterpret_cast<ho::cx<double>*>(out->peer_r[p][k]);
-    }
   if (out->n_rebuild < 0 || out->n_rebuild > HO_MAX_PEERS) return fail(HO_ERR_BAD_ARGUMENT, "n_rebuild must be 0 .. HO_MAX_PEERS");
-  o.n_rebuild = out->n_rebuild;
-  for (int p = 0; p < o.n_rebuild; ++p) {
-    if (out->rebuild_n[p] < 0 || out->rebuild_n[p] > n_end - n_begin)
-      return fail(HO_ERR_BAD_ARGUMENT, "rebuild_n must be 0 .. n_end - n_begin (thread i of the launch handles element i)");
-    if (!out->rebuild_mueller[p]) return fail(HO_ERR_BAD_ARGUMENT, "rebuild_mueller: NULL destination");
-    o.rebuild_n[p] = out->rebuild_n[p];
-    o.rebuild_mueller[p] = out->rebuild_mueller[p];
-    for (int k = 0; k < 4; ++k) {
-      if (!out->rebuild_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "rebuild_r: NULL source");
-      o.rebuild_r[p][k] = reinterpret_cast<const ho::cx<double>*>(out->rebuild_r[p][k]);
+  static thread_local Gather<double, true> g;   // (1.2 KB: kept off the stack of the plain path)
+  const bool gathering = out->n_peers > 0 || out->n_rebuild > 0;
+  if (gathering) {
+    if (o.power || o.t_pp) return fail(HO_ERR_BAD_ARGUMENT, "peer_r / rebuild_* need a launch without power and transmission outputs");
+    if (problem->T > 1) return fail(HO_ERR_BAD_ARGUMENT, "peer_r / rebuild_* are not supported on a thickness sweep");
+    g.n_peers = out->n_peers;
+    for (int p = 0; p < g.n_peers; ++p)
+      for (int k = 0; k < 4; ++k) {
+        if (!out->peer_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "peer_r: NULL destination");
+        g.peer[p][k] = reinterpret_cast<ho::cx<double>*>(out->peer_r[p][k]);
+      }
+    g.n_rebuild = out->n_rebuild;
+    for (int p = 0; p < g.n_rebuild; ++p) {
+      if (out->rebuild_n[p] < 0 || out->rebuild_n[p] > n_end - n_begin)
+        return fail(HO_ERR_BAD_ARGUMENT, "rebuild_n must be 0 .. n_end - n_begin (thread i of the launch handles element i)");
+      if (!out->rebuild_mueller[p]) return fail(HO_ERR_BAD_ARGUMENT, "rebuild_mueller: NULL destination");
+      g.rebuild_n[p] = out->rebuild_n[p];
+      g.rebuild_mueller[p] = out->rebuild_mueller[p];
+      for (int k = 0; k < 4; ++k) {
+        if (!out->rebuild_r[p][k]) return fail(HO_ERR_BAD_ARGUMENT, "rebuild_r: NULL source");
+        g.rebuild_r[p][k] = reinterpret_cast<const ho::cx<double>*>(out->rebuild_r[p][k]);
+      }
     }
   }
-  if (o.n_rebuild > 0 && problem->T > 1) return fail(HO_ERR_BAD_ARGUMENT, "rebuild ranges are not supported on a thickness sweep");
   DeviceScope scope(problem->kx);
   if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  return problem->backend == HO_BACKEND_SCATTERING ? launch<double, true>(problem, o, n_begin, n_end, s)
-                                                   : launch<double, false>(problem, o, n_begin, n_end, s);
+  return problem->backend == HO_BACKEND_SCATTERING ? launch<double, true>(problem, o, gathering ? &g : nullptr, n_begin, n_end, s)
+                                                   : launch<double, false>(problem, o, gathering ? &g : nullptr, n_begin, n_end, s);
 }
 
 int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int64_t n_begin, int64_t n_end, void* cuda_stream) {
@@ -869,13 +900,11 @@ int ho_reflect_f32(const ho_problem_t* problem, const ho_outputs_f32_t* out, int
   o.t_mode = nullptr;
   o.t_mode_stride = 0;
   o.power_states = 2;
-  o.n_peers = 0;
-  o.n_rebuild = 0;
   DeviceScope scope(problem->kx);
   if (!scope.ok) return fail(HO_ERR_NO_DEVICE, "cannot select the device that owns the problem tables");
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, n_begin, n_end, s)
-                                                   : launch<float, false>(problem, o, n_begin, n_end, s);
+  return problem->backend == HO_BACKEND_SCATTERING ? launch<float, true>(problem, o, nullptr, n_begin, n_end, s)
+                                                   : launch<float, false>(problem, o, nullptr, n_begin, n_end, s);
 }
 
 int ho_measure_fp64_peak(int iters, double* flops_per_s, void* cuda_stream) {

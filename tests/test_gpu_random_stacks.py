@@ -298,3 +298,111 @@ def test_untilted_random_stacks_match_oracle(block, forced, built_library):
                 worst = max(worst, float(err[ok].max()))
     assert hinted >= 40   # every stack of this generator is un-tilted
     print(f"block {block} ({forced}): worst Jones rel err {worst:.2e}, {hinted} hinted runs, {two_launch} two-launch runs")
+
+
+def uniaxial_case(seed):
+    """Stacks of UNIAXIAL crystals at generic orientations: the plans whose layers take the factorised
+    quartic (ho_layer_t.eps_ordinary: split_uniaxial for exits and thick films, the ordinary /
+    extraordinary pair form for thin films).  Built-in uniaxial materials, weakly and strongly lossy
+    arbitrary uniaxial tensors, and
+    a scalar mu != 1; thin and thick films; FullSweep / Incident / Azimuthal grids.  (Weakly lossy, not
+    lossless, arbitrary tensors: for exactly real tensors with mixed real / complex modes the reference's
+    slot-wise sort is broken, SURVEY 7.0-3, and there is no oracle to compare with.)"""
+    rng = np.random.default_rng(seed)
+    built_in = {"Quartz": (420.0, 590.0), "Calcite": (1320.0, 1580.0), "hBN": (750.0, 1650.0), "Sapphire": (300.0, 1000.0)}
+
+    def arbitrary():
+        weak = rng.random() < 0.4
+        im = (lambda: float(10 ** rng.uniform(-4, -2))) if weak else (lambda: float(rng.uniform(0.05, 1.0)))
+        eo = {"real": float(rng.uniform(-6, 8)), "imag": im()}
+        ee = {"real": float(rng.uniform(1, 9)), "imag": im()}
+        axis = int(rng.integers(3))   # which principal axis carries the extraordinary value
+        spec = {f"eps_{k}": (ee if i == axis else eo) for i, k in enumerate(("xx", "yy", "zz"))}
+        if rng.random() < 0.5:
+            spec["mu_r"] = float(rng.uniform(0.7, 2.0))
+        return spec
+
+    def material(band):
+        if rng.random() < 0.35:
+            return arbitrary(), band
+        name = list(built_in)[int(rng.integers(len(built_in)))]
+        lo, hi = built_in[name]
+        if band is not None:
+            lo2, hi2 = max(lo, band[0]), min(hi, band[1])
+            if lo2 < hi2:
+                lo, hi = lo2, hi2
+            else:
+                return arbitrary(), band
+        return name, (lo, hi)
+
+    band = None
+    layers = [P.prism(float(rng.uniform(4.0, 40.0)))]
+    if rng.random() < 0.4:
+        layers.append(P.gap(float(10 ** rng.uniform(-2, 0)), 1.0))
+    for _ in range(int(rng.integers(0, 3))):
+        m, band = material(band)
+        layers.append(P.film(m, float(10 ** rng.uniform(-2, 0.8)), rx=_angle(rng), ry=float(rng.uniform(0, 180)), rz=_angle(rng)))
+    m, band = material(band)
+    layers.append(P.substrate(m, rx=_angle(rng), ry=float(rng.uniform(0, 180)), rz=_angle(rng)))
+    lo, hi = band if band is not None else (600.0, 1200.0)
+    freqs = list(np.sort(rng.uniform(lo, hi, 4)))
+    kind = ["Incident", "Azimuthal", "FullSweep"][int(rng.integers(3))]
+    if kind == "Incident":
+        sd, grid = {"type": kind, "frequency": freqs}, dict(A=32)
+    elif kind == "Azimuthal":
+        sd, grid = {"type": kind, "incidentAngle": float(rng.uniform(5, 85)), "frequency": freqs}, dict(B=32)
+    else:
+        sd, grid = {"type": kind, "frequency": freqs}, dict(A=10, B=10)
+    return {"payload": {"ScenarioData": sd, "Layers": layers}, "grid": grid}
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_uniaxial_closed_forms_match_oracle(block, built_library):
+    """Both recursions, WITHOUT power outputs (the scale-free cubic and, with the two-launch
+    protocol forced, the lean / fast builds + fix-up pass) and with them (exact scale, general
+    build), against the reference's stable backend, unmasked."""
+    from hyperbolic_optics_b200.plan import build_plan
+    from hyperbolic_optics_b200.scenario import ScenarioSetup
+    from oracle import reference_port as oracle
+
+    worst, n_points, n_hinted = 0.0, 0, 0
+    for seed in range(9000 + 20 * block, 9000 + 20 * (block + 1)):
+        entry = uniaxial_case(seed)
+        inc, az = P.angle_overrides(entry)
+        try:
+            ref = oracle.run(entry["payload"], backend="scattering", incident_angle=inc, azimuthal_angle=az)
+        except np.linalg.LinAlgError:
+            continue
+        plan = build_plan(ScenarioSetup(entry["payload"]["ScenarioData"]), entry["payload"]["Layers"])
+        n_hinted += sum(lp.eps_ordinary is not None for lp in plan.layers)
+        for backend in ("scattering", "transfer"):
+            for protocol, power in (("auto", False), ("fast", False), ("auto", True)):
+                from hyperbolic_optics_b200 import Structure
+
+                s = Structure(device="cuda:0", protocol=protocol)
+                s.get_scenario(entry["payload"]["ScenarioData"])
+                if inc is not None:
+                    s.scenario.incident_angle = inc
+                if az is not None:
+                    s.scenario.azimuthal_angle = az
+                s.setup_attributes()
+                s.get_layers(entry["payload"]["Layers"])
+                s.with_power = power
+                if backend == "transfer":
+                    s.calculate()
+                    s.calculate_reflectivity()
+                else:
+                    s.calculate_scattering()
+                got = {k: getattr(s, k) for k in parity.R_KEYS}
+                err = parity.jones_error(got, ref)
+                mask = np.isfinite(err)
+                if backend == "scattering":
+                    assert np.isfinite(np.stack([got[k] for k in parity.R_KEYS])).all(), f"seed {seed}: non-finite stable result"
+                    assert mask.mean() > 0.9, f"seed {seed}"
+                if mask.any():
+                    assert err[mask].max() <= 1e-9, (f"seed {seed} {backend} protocol={protocol} power={power}: "
+                                                     f"{err[mask].max():.3e}\n{entry['payload']}")
+                    worst = max(worst, float(err[mask].max()))
+                n_points += int(mask.sum())
+    assert n_hinted > 0
+    print(f"uniaxial block {block}: {n_points} point evaluations, {n_hinted} hinted layers, worst Jones rel err {worst:.2e}")

@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--json", default="")
     ap.add_argument("--dtype", default="c128", choices=["c128", "c64"], help="c64: the opt-in complex64 kernels")
+    ap.add_argument("--tsweep-groups", default="0", help="comma list: groups per warp of the thickness-sweep kernel (0 = library's choice)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     want = [s for s in args.only.split(",") if s]
@@ -79,8 +80,9 @@ def main():
         planes = 2 * (len(plan.layers) + 1) if (power and args.dtype == "c128") else 0
         out = engine.DeviceOutputs(n, dev, mueller=True, power_planes=planes,
                                    dtype=torch.complex128 if args.dtype == "c128" else torch.complex64)
-        for backend in backends:
-            prob = engine.DeviceProblem(plan, backend, dev)
+        gpws = [int(g) for g in args.tsweep_groups.split(",")] if plan.T > 1 else [0]
+        for backend, gpw in [(b, g) for b in backends for g in gpws]:
+            prob = engine.DeviceProblem(plan, backend, dev, tsweep_groups=gpw)
             for _ in range(3):
                 engine.reflect(prob, out)
             torch.cuda.synchronize()
@@ -93,7 +95,7 @@ def main():
             ms = e0.elapsed_time(e1) / args.reps
             finite = float(torch.isfinite(torch.view_as_real(out.r)).all(dim=(0, 2)).double().mean().item())
             row = {"config": name, "backend": backend, "dtype": args.dtype, "shape_FABT": list(plan.fabt_shape), "points": n,
-                   "layers_below_prism": len(plan.layers), "power": power, "kernel_ms": ms,
+                   "layers_below_prism": len(plan.layers), "power": power, "tsweep_groups": gpw, "kernel_ms": ms,
                    "points_per_s": n / (ms * 1e-3), "finite_fraction": finite}
             rows.append(row)
             print(json.dumps(row), flush=True)
