@@ -1,10 +1,10 @@
 #!/bin/bash
 # One round's ncu evidence (run under gpurun, 1 GPU):  bash tools/ncu_round.sh <tag> [what ...]
-#   what: c4 c4_scat tilted tilted_scat tsweep polar launches   (default: all)
+#   what: c4 c4_scat aniso tilted tilted_scat tsweep polar launches   (default: all)
 # Each capture is `ncu --set full --clock-control none --import-source on` of exactly one timed step
 # (warm-up launches skipped); reports land in gpurun_out/<tag>_<what>.ncu-rep.
 tag=$1; shift
-what=${@:-c4 c4_scat tilted tilted_scat tsweep polar launches}
+what=${@:-c4 c4_scat aniso tilted tilted_scat tsweep polar launches}
 NCU="ncu --set full --clock-control none --import-source on"
 CB="python tools/config_bench.py --reps 1"
 for w in $what; do
@@ -12,6 +12,7 @@ for w in $what; do
     # fast-path protocol: 2 launches per reflect (fast build + fix-up); 3 warm-ups + 1 timed per backend
     c4)          $NCU -k regex:reflect_kernel -s 6  -c 2 -o gpurun_out/${tag}_c4          -f $CB --only c4 ;;
     c4_scat)     $NCU -k regex:reflect_kernel -s 14 -c 2 -o gpurun_out/${tag}_c4_scat     -f $CB --only c4 ;;
+    aniso)       $NCU -k regex:reflect_kernel -s 6  -c 2 -o gpurun_out/${tag}_aniso       -f $CB --only c4_aniso ;;
     # lean build + fix-up: 2 launches per reflect, as c4
     tilted)      $NCU -k regex:reflect_kernel -s 6  -c 2 -o gpurun_out/${tag}_tilted      -f $CB --only c4_tilted ;;
     tilted_scat) $NCU -k regex:reflect_kernel -s 14 -c 2 -o gpurun_out/${tag}_tilted_scat -f $CB --only c4_tilted ;;
