@@ -10,7 +10,7 @@ if [ $stage = ncu ]; then
   ( time timeout 1100 python -m pytest tests -m gpu -q --maxfail=8 --durations=12 ) > gpurun_out/${tag}_pytest.log 2>&1
   echo "pytest rc=$? $(tail -5 gpurun_out/${tag}_pytest.log | head -1)"
   timeout 300 python tools/config_bench.py --json gpurun_out/${tag}_config_bench.jsonl > gpurun_out/${tag}_config_bench.log 2>&1; echo "cfg rc=$?"
-  timeout 200 python tools/config_bench.py --dtype c64 --only c1,c4,c4_tilted --json gpurun_out/${tag}_config_bench_c64.jsonl > gpurun_out/${tag}_config_bench_c64.log 2>&1; echo "cfg64 rc=$?"
+  timeout 200 python tools/config_bench.py --dtype c64 --only c4 --json gpurun_out/${tag}_config_bench_c64.jsonl > gpurun_out/${tag}_config_bench_c64.log 2>&1; echo "cfg64 rc=$?"
   timeout 200 python tools/polarimetry_bench.py --json gpurun_out/${tag}_polarimetry_bench.jsonl > gpurun_out/${tag}_polarimetry_bench.log 2>&1; echo "pol rc=$?"
   timeout 900 bash tools/ncu_round.sh ${tag} > gpurun_out/${tag}_ncu_round.log 2>&1; echo "ncu rc=$?"
   tail -12 gpurun_out/${tag}_ncu_round.log

@@ -4,7 +4,7 @@
 # Each capture is `ncu --set full --clock-control none --import-source on` of exactly one timed step
 # (warm-up launches skipped); reports land in gpurun_out/<tag>_<what>.ncu-rep.
 tag=$1; shift
-what=${@:-c4 c4_scat aniso tilted tilted_scat tsweep polar launches}
+what=${@:-c4 c4_scat aniso tilted tsweep polar launches}
 NCU="ncu --set full --clock-control none --import-source on"
 CB="python tools/config_bench.py --reps 1"
 for w in $what; do
@@ -28,9 +28,8 @@ for w in $what; do
   rep=gpurun_out/${tag}_${w}.ncu-rep
   if [ -f $rep ]; then
     ncu -i $rep --page raw --csv > gpurun_out/${tag}_${w}_raw.csv 2>/dev/null
-    ncu -i $rep --page source --csv > gpurun_out/${tag}_${w}_source.csv 2>/dev/null
-    ncu -i $rep --page source --csv --print-source cuda,sass > gpurun_out/${tag}_${w}_srcsass.csv 2>/dev/null
-    ncu -i $rep --page details > gpurun_out/${tag}_${w}_details.txt 2>/dev/null
+    ncu -i $rep --page source --csv | gzip -9 > gpurun_out/${tag}_${w}_source.csv.gz 2>/dev/null
+    ncu -i $rep --page source --csv --print-source cuda,sass | gzip -9 > gpurun_out/${tag}_${w}_srcsass.csv.gz 2>/dev/null
     [ -z "$HO_KEEP_REP" ] && rm -f $rep
   fi
 done
