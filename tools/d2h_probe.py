@@ -40,7 +40,9 @@ def main():
     sets = [[0]] + [list(range(k)) for k in (2, 4, 8) if k <= n]
     if n >= 8:
         sets += [[0, 4], [0, 7], [2, 3], [4, 5, 6, 7]]
-    for direction in ("d2h", "h2d"):
+    import sys
+
+    for direction in (sys.argv[1:] or ["d2h", "h2d"]):
         for devs in sets:
             gbs = run(devs, direction)
             print(json.dumps({"direction": direction, "gpus": devs, "aggregate_GBps": round(gbs, 1),

@@ -16,4 +16,4 @@ print({k:g.get(k) for k in ("ms_per_step","transport","transport_error","GBps_re
 print("weak", (d.get("weak") or {}).get("value"))
 PY
 if [ $n -eq 2 ]; then timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "owns_the_buffers" 2>&1 | tail -2; fi
-if [ -n "$HO_D2H_PROBE" ]; then timeout 200 python tools/d2h_probe.py > gpurun_out/${tag}_d2h_probe_${n}gpu.txt 2>&1; tail -15 gpurun_out/${tag}_d2h_probe_${n}gpu.txt; fi
+if [ -n "$HO_D2H_PROBE" ]; then timeout 200 python tools/d2h_probe.py d2h > gpurun_out/${tag}_d2h_probe_${n}gpu.txt 2>&1; tail -15 gpurun_out/${tag}_d2h_probe_${n}gpu.txt; fi
