@@ -590,13 +590,66 @@ template <typename T, bool SCALE_FREE> __device__ __forceinline__ bool film_thin
   return true;
 }
 
+// The same for the plane an isotropic exit (or isotropic crystal exit) leaves behind,
+//   y0 = (0, p, q, 0),  y1 = (r, 0, 0, s)   (the s and the p wave: exit_iso_plane, iso_crystal_exit_plane):
+// the first mat-vec and the first accumulation only touch the non-zero entries -- 4 + 6 instead of
+// 10 + 10 complex products (non-magnetic Delta) -- and, for y1 with a scalar mu, the second mat-vec
+// skips the row that is still zero.  Every film that sits directly on such an exit takes this.
+template <typename T, bool NM> __device__ __forceinline__ void cubic_apply_sparse(const Delta<T, NM>& D, cx<T> a0, cx<T> a1, cx<T> a2, cx<T> a3, Vec4<T>& y0, Vec4<T>& y1) {
+  {  // y0 = (0, p, q, 0)
+    const cx<T> p = y0.v1, q = y0.v2;
+    Vec4<T> v;
+    if constexpr (NM) {
+      v.v0 = D.b * p; v.v1 = D.f * q; v.v2 = D.h * p; v.v3 = -(D.g * p);
+    } else {
+      v.v0 = fma(D.c, q, D.b * p); v.v1 = fma(D.f, q, D.e * p); v.v2 = fma(D.e, q, D.h * p); v.v3 = -(D.g * p);
+    }
+    Vec4<T> o;
+    o.v0 = a1 * v.v0; o.v1 = fma(a1, v.v1, a0 * p); o.v2 = fma(a1, v.v2, a0 * q); o.v3 = a1 * v.v3;
+    v = matvec(D, v);
+    o = axpy(a2, v, o);
+    v = matvec(D, v);
+    y0 = axpy(a3, v, o);
+  }
+  {  // y1 = (r, 0, 0, s)
+    const cx<T> r = y1.v0, t = y1.v3;
+    Vec4<T> v;
+    v.v0 = fma(D.d, t, D.a * r);
+    v.v2 = fnma(D.b, t, D.g * r);
+    v.v3 = fma(D.a, t, D.j * r);
+    Vec4<T> o;
+    o.v0 = fma(a1, v.v0, a0 * r); o.v2 = a1 * v.v2; o.v3 = fma(a1, v.v3, a0 * t);
+    if constexpr (NM) {
+      // v.v1 = 0: second mat-vec without the column that multiplies it
+      Vec4<T> u;
+      u.v0 = fma(D.d, v.v3, D.a * v.v0);
+      u.v1 = D.f * v.v2;
+      u.v2 = fnma(D.b, v.v3, D.g * v.v0);
+      u.v3 = fma(D.a, v.v3, D.j * v.v0);
+      o.v0 = fma(a2, u.v0, o.v0); o.v1 = a2 * u.v1; o.v2 = fma(a2, u.v2, o.v2); o.v3 = fma(a2, u.v3, o.v3);
+      v = matvec(D, u);
+    } else {
+      v.v1 = -(D.c * t);
+      o.v1 = a1 * v.v1;
+      v = matvec(D, v);
+      o = axpy(a2, v, o);
+      v = matvec(D, v);
+    }
+    y1 = axpy(a3, v, o);
+  }
+}
+
 // The cubic applied to the running plane; stable recursion: then re-based to unit (Ex, Ey) rows,
 // which keeps the basis well conditioned so that the <= 2.6 digits the cubic costs do not compound
 // over layers (W = the re-basing matrix, for the power bookkeeping).
 template <typename T, bool NM, bool STABLE> __device__ __forceinline__ void film_cubic(const Delta<T, NM>& D, cx<T> a0, cx<T> a1, cx<T> a2, cx<T> a3,
-                                                                                Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4]) {
-  cubic_apply(D, a0, a1, a2, a3, y0);
-  cubic_apply(D, a0, a1, a2, a3, y1);
+                                                                                Vec4<T>& y0, Vec4<T>& y1, cx<T> w[4], bool sparse = false) {
+  if (sparse) {
+    cubic_apply_sparse(D, a0, a1, a2, a3, y0, y1);
+  } else {
+    cubic_apply(D, a0, a1, a2, a3, y0);
+    cubic_apply(D, a0, a1, a2, a3, y1);
+  }
   if constexpr (STABLE) {
     inv2(y0.v0, y1.v0, y0.v1, y1.v1, w[0], w[1], w[2], w[3]);
     Vec4<T> t0 = axpy(w[2], y1, scale(w[0], y0));

@@ -120,15 +120,25 @@ template <typename T, bool NM> __device__ __forceinline__ ho::Delta<T, NM> layer
 // FAST == 2: lean build for tilted plans (general start values, thin films as one cubic in Delta; no
 // pair-symmetric form, no block / thick-film code).  Both set `bail` when the point needs the
 // general build (FAST == 0), which compiles everything.
-template <typename T, bool STABLE, bool NM, bool EXTRAS, int FAST = 0>
+template <typename T, bool STABLE, bool NM, bool EXTRAS, int FAST = 0, bool SPARSE = false>
 __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int f, int a, int b, int t,
                                             ho::Vec4<T>& y0, ho::Vec4<T>& y1, ho::cx<T> w[4], ho::cx<T> binv[4],
-                                            bool& bail, bool untilted = true) {
+                                            bool& bail, bool untilted = true, bool* sparse = nullptr) {
   using namespace ho;
+  // SPARSE builds (the host picks them for stacks whose crystal film sits directly on an isotropic
+  // exit; a separate instantiation because the extra code cost the other stacks up to 10 %):
+  // `*sparse` = the running plane still has the zero pattern of that exit, y0 = (0, p, q, 0),
+  // y1 = (r, 0, 0, s); set by the exit, used (and cleared) by the film directly above it
+  bool sparse_in = false;
+  if constexpr (SPARSE) {
+    sparse_in = *sparse;
+    *sparse = false;
+  }
   // isotropic crystal (scalar eps(f), mu(f), e.g. SiC): closed-form modes, no quartic
   const bool iso_crystal = (L.kind == HO_ANISO_FILM || L.kind == HO_ANISO_EXIT) && L.eps_scalar && L.mu_scalar;
   if (L.kind == HO_ISO_EXIT) {
     exit_iso_plane(ldc<T>(L.exit_cos + a), T(L.exit_n), y0, y1);
+    if constexpr (SPARSE) *sparse = true;
     if constexpr (EXTRAS) { binv[0] = mk<T>(T(1), T(0)); binv[1] = mk<T>(T(0), T(0)); binv[2] = binv[1]; binv[3] = binv[0]; }
   } else if (L.kind == HO_ISO_FILM || iso_crystal) {
     // scalar medium: constants of the descriptor (isotropic film) or row f of the tables (crystal)
@@ -139,6 +149,7 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
     }
     if (L.kind == HO_ANISO_EXIT) {
       iso_crystal_exit_plane(k, eps, mu, y0, y1);
+      if constexpr (SPARSE) *sparse = true;
       // transmission amplitudes of a degenerate exit: (Ex, Ey) of the transmitted field, as in exit_mode_basis
       if constexpr (EXTRAS) { binv[0] = y0.v0; binv[1] = y1.v0; binv[2] = y0.v1; binv[3] = y1.v1; }
     } else {
@@ -209,7 +220,8 @@ __device__ __forceinline__ void apply_layer(const ho_layer_t& L, T k, T k0, int 
         }
       }
     }
-    film_cubic<T, NM, STABLE>(D, a0, a1, a2, a3, y0, y1, w);
+    if constexpr (SPARSE) film_cubic<T, NM, STABLE>(D, a0, a1, a2, a3, y0, y1, w, sparse_in);
+    else film_cubic<T, NM, STABLE>(D, a0, a1, a2, a3, y0, y1, w);
   }
 }
 
@@ -393,7 +405,7 @@ template <typename T> __device__ __forceinline__ void rebuild_received(const Gat
 // POWER: additionally R, T and the layer-resolved absorption for p and s incidence.
 // FAST: see above.  mode: MODE_ALL, or MODE_FIXUP = only the deferred points.
 // work[0] = number of deferred points, work[1 .. cap] = their indices relative to n_begin.
-template <typename T, bool STABLE, bool NM, bool POWER, int FAST, bool GATHER = false>
+template <typename T, bool STABLE, bool NM, bool POWER, int FAST, bool GATHER = false, bool SPARSE = false>
 __global__ void __launch_bounds__(kThreads, FAST ? HO_FAST_BLOCKS : HO_MIN_BLOCKS)
 reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n_begin, int64_t n_end, int mode,
                unsigned* work, unsigned cap, const __grid_constant__ Gather<T, GATHER> gather) {
@@ -440,11 +452,11 @@ reflect_kernel(const __grid_constant__ ho_problem_t P, OutPtrs<T> out, int64_t n
     T hf[POWER ? HO_MAX_LAYERS : 1][4];
     cx<T> wm[POWER ? HO_MAX_LAYERS : 1][4];
     cx<T> binv[4];
-    bool bail = false;
+    bool bail = false, sparse = false;
 #pragma unroll 1
     for (int l = P.n_layers - 1; l >= 0; --l) {
       cx<T> w[4];
-      apply_layer<T, STABLE, NM, POWER, FAST>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path == HO_HINT_UNTILTED && mode != MODE_FIXUP);
+      apply_layer<T, STABLE, NM, POWER, FAST, SPARSE>(P.layers[l], k, k0, f, a, b, t, y0, y1, w, binv, bail, P.hint_fast_path == HO_HINT_UNTILTED && mode != MODE_FIXUP, &sparse);
       if constexpr (FAST != 0) {
         if (bail) break;
       }
@@ -776,10 +788,27 @@ int launch_k(const ho_problem_t* p, const OutPtrs<T>& out, const Gather<T, GATHE
       const int64_t cap = p->work_capacity < (int64_t)0x7fffffff ? p->work_capacity : (int64_t)0x7fffffff;
       if (cudaMemsetAsync(p->work, 0, sizeof(unsigned), stream) != cudaSuccess)
         return fail(HO_ERR_CUDA, "work list reset failed: %s", cudaGetErrorString(cudaGetLastError()));
+      // a crystal film directly on an isotropic exit (or isotropic crystal): the build whose first
+      // film mat-vec knows the zero pattern of that exit's plane
+      bool sparse = false;
+      if (p->n_layers >= 2) {
+        const ho_layer_t& ex = p->layers[p->n_layers - 1];
+        const ho_layer_t& fl = p->layers[p->n_layers - 2];
+        const bool iso_exit = ex.kind == HO_ISO_EXIT || (ex.kind == HO_ANISO_EXIT && ex.eps_scalar && ex.mu_scalar);
+        sparse = iso_exit && fl.kind == HO_ANISO_FILM && !(fl.eps_scalar && fl.mu_scalar);
+      }
       if (p->hint_fast_path == HO_HINT_TILTED_THIN) {   // lean build: general start values, thin films only
-        const void* lean = (const void*)reflect_kernel<T, STABLE, NM, false, 2, GATHER>;
-        reflect_kernel<T, STABLE, NM, false, 2, GATHER><<<grid_for(n, lean, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
-      } else {                                          // fast build: un-tilted crystals
+        if (sparse) {
+          const void* lean = (const void*)reflect_kernel<T, STABLE, NM, false, 2, GATHER, true>;
+          reflect_kernel<T, STABLE, NM, false, 2, GATHER, true><<<grid_for(n, lean, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
+        } else {
+          const void* lean = (const void*)reflect_kernel<T, STABLE, NM, false, 2, GATHER>;
+          reflect_kernel<T, STABLE, NM, false, 2, GATHER><<<grid_for(n, lean, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
+        }
+      } else if (sparse) {                              // fast build: un-tilted crystals
+        const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, 1, GATHER, true>;
+        reflect_kernel<T, STABLE, NM, false, 1, GATHER, true><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
+      } else {
         const void* fast = (const void*)reflect_kernel<T, STABLE, NM, false, 1, GATHER>;
         reflect_kernel<T, STABLE, NM, false, 1, GATHER><<<grid_for(n, fast, p->max_ctas_per_sm), kThreads, 0, stream>>>(*p, out, n_begin, n_end, MODE_ALL, p->work, (unsigned)cap, gather);
       }
