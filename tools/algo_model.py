@@ -781,3 +781,93 @@ def film_pair_symmetric(D, Y, cfac):
         v3 = matvec(D, v2)
         out.append(tuple(a0 * y[i] + a1 * v1[i] + a2 * v2[i] + a3 * v3[i] for i in range(4)))
     return out, ok
+
+
+# ----------------------------------------------------------------------------- uniaxial crystals: factorised quartic
+def _cosh_sinhc_w(w):
+    """cosh(sqrt(w)) and sinh(sqrt(w))/sqrt(w) as entire functions of w (model of ho_berreman.cuh
+    cosh_sinhc_pair / cosh_sinhc_w): Taylor series in w below |w| = 1 -- seven terms below 0.1, ten
+    below 1 -- and the exponential form above; no complex square root on the series path."""
+    import math
+
+    w = np.asarray(w, dtype=complex)
+    ca = [1.0 / math.factorial(2 * k) for k in range(9, -1, -1)]
+    cb = [1.0 / math.factorial(2 * k + 1) for k in range(9, -1, -1)]
+
+    def horner(first):
+        a, b = np.full(w.shape, ca[first], dtype=complex), np.full(w.shape, cb[first], dtype=complex)
+        for i in range(first + 1, 10):
+            a, b = w * a + ca[i], w * b + cb[i]
+        return a, b
+
+    a7, b7 = horner(3)
+    a10, b10 = horner(0)
+    big = np.abs(w) >= 1.0
+    z = np.sqrt(np.where(big, w, 1.0))
+    e = np.exp(z)
+    ei = 1.0 / e
+    tiny = np.abs(w) < 0.1
+    ch = np.where(big, 0.5 * (e + ei), np.where(tiny, a7, a10))
+    sh = np.where(big, 0.5 * (e - ei) / z, np.where(tiny, b7, b10))
+    return ch, sh
+
+
+def _thin_pair(re_cm, w, limit=3.0):
+    """|Re(c m)| + |Re sqrt(w)| < limit without the square root (ho_berreman.cuh thin_pair)."""
+    lim = limit - np.abs(re_cm)
+    r = 2.0 * lim * lim - np.real(w)
+    return (lim > 0) & (r > 0) & (np.abs(w) ** 2 < r * r)
+
+
+def uniaxial_split(c3, c2, qo):
+    """Spectral split of a uniaxial crystal (model of ho_berreman.cuh split_uniaxial): the quartic
+    factorises exactly, (x^2 + q_o)(x^2 + c3 x + q_e), q_o = kx^2 - mu eps_o, q_e = c2 - q_o; the four
+    roots are two square roots away, the forward pair follows from the reference's rule on them.
+    -> (sf, pf, sb, pb)."""
+    lo = np.sqrt(-qo + 0j)
+    le0, le1 = _quad_roots(c3, c2 - qo)
+    roots = [lo, -lo, le0, le1]
+    fwd, _ = classify_forward(roots)
+    sf = sum(np.where(m, lam, 0.0) for m, lam in zip(fwd, roots))
+    pf = np.prod([np.where(m, lam, 1.0) for m, lam in zip(fwd, roots)], axis=0)
+    sb = sum(np.where(m, 0.0, lam) for m, lam in zip(fwd, roots))
+    pb = np.prod([np.where(m, 1.0, lam) for m, lam in zip(fwd, roots)], axis=0)
+    return sf, pf, sb, pb
+
+
+def film_pair_uniaxial(D, Y, cfac, qo):
+    """exp(cfac D) Y for a thin film of a uniaxial crystal at ANY orientation (model of
+    ho_berreman.cuh pair_factors_uniaxial + pair_symmetric_film_coeffs): the ordinary pair +-mu_o
+    (mu_o^2 = -q_o) and the extraordinary pair -c3/2 +- mu_e are known in closed form, so the cubic
+    needs neither a split nor the odd quartic coefficients.  Returns (columns, ok)."""
+    c3, c2, _, _ = charpoly(D)
+    sf, pf, sb, pb = np.zeros_like(c3), qo + 0 * c3, -c3, c2 - qo
+    d0, d1 = 0.5 * sf, 0.5 * sb
+    m0, m1 = d0 * d0 - pf, d1 * d1 - pb
+    ok = np.abs(m0 - m1) ** 2 >= PAIR_SEPARATION * (np.abs(m0) ** 2 + np.abs(m1) ** 2)
+    cc = cfac * cfac
+    w0, w1 = cc * m0, cc * m1
+    x1 = cfac * d1
+    ok = ok & _thin_pair(0.0, w0) & _thin_pair(np.real(x1), w1)
+    A0, S0 = _cosh_sinhc_w(w0)
+    A1, S1 = _cosh_sinhc_w(w1)
+    e1 = np.where(np.abs(x1) ** 2 < 1e-10, 1 + x1 * (1 + 0.5 * x1), np.exp(x1))
+    B0, B1 = cfac * S0, e1 * cfac * S1
+    A1 = e1 * A1
+    af0, af1 = A0 - B0 * d0, B0
+    ab0, ab1 = A1 - B1 * d1, B1
+    h0, h1 = projector_coeffs(sf, pf, sb, pb)
+    e0_, e1_ = af0 - ab0, af1 - ab1
+    g0, g1, g2 = e0_ * h0, e0_ * h1 + e1_ * h0, e1_ * h1
+    q3, q2, q1, q0 = -(sf + sb), sf * sb + pf + pb, -(sf * pb + sb * pf), pf * pb   # q_0 q_1
+    a3 = g1 - sb * g2 - g2 * q3
+    a2 = g0 - sb * g1 + pb * g2 - g2 * q2
+    a1 = -sb * g0 + pb * g1 - g2 * q1 + ab1
+    a0 = pb * g0 - g2 * q0 + ab0
+    out = []
+    for y in Y:
+        v1 = matvec(D, y)
+        v2 = matvec(D, v1)
+        v3 = matvec(D, v2)
+        out.append(tuple(a0 * y[i] + a1 * v1[i] + a2 * v2[i] + a3 * v3[i] for i in range(4)))
+    return out, ok

@@ -33,7 +33,17 @@ def layer_delta(plan, lp, f, a, b):
     return am.berreman9(k + 0j, e, m)
 
 
-def run(plan, backend="transfer", stats=None, **kw):
+def _ordinary_factor(plan, lp, f, k):
+    """q_o = kx^2 - mu eps_o of a uniaxial layer (plan.eps_ordinary), else None."""
+    if getattr(lp, "eps_ordinary", None) is None:
+        return None
+    eo = _pick(lp.eps_ordinary.reshape(-1, 1), f)[..., 0]
+    mu = _pick(lp.mu, f)[..., 0]
+    return k * k - mu * eo
+
+
+def run(plan, backend="transfer", stats=None, uniaxial=True, **kw):
+    """`uniaxial=False`: ignore the uniaxial hint (the general split on every layer)."""
     f, a, b, t = _grid(plan)
     k = plan.kx[a] + 0j
     k0 = plan.k0[f]
@@ -49,9 +59,15 @@ def run(plan, backend="transfer", stats=None, **kw):
                 continue
             if lp.kind == P.KIND_ANISO_EXIT:
                 D = layer_delta(plan, lp, f, a, b)
-                spec = am.split_spectrum(D, stats=stats, **kw)
-                if stats is not None:
-                    stats.setdefault("n_complex", []).append(spec[4])
+                qo = _ordinary_factor(plan, lp, f, k)
+                if qo is not None and uniaxial:
+                    # uniaxial crystal: forward / backward pairs straight from the factorised quartic
+                    c3, c2, _, _ = am.charpoly(D)
+                    spec = am.uniaxial_split(c3, c2, qo) + (None,)
+                else:
+                    spec = am.split_spectrum(D, stats=stats, **kw)
+                    if stats is not None:
+                        stats.setdefault("n_complex", []).append(spec[4])
                 Y = am.substrate_plane(D, spec[:4])
                 forms.append(am.flux_form(Y)); maps.append(None)
                 continue
@@ -67,17 +83,22 @@ def run(plan, backend="transfer", stats=None, **kw):
                     Y = am.iso_film_transfer(k, eps, mu, Y, cfac)
             else:
                 D = layer_delta(plan, lp, f, a, b)
-                spec = am.split_spectrum(D, stats=stats, **kw)
-                if stats is not None:
-                    stats.setdefault("n_complex", []).append(spec[4])
+                qo = _ordinary_factor(plan, lp, f, k) if uniaxial else None
+                if qo is not None:
+                    c3, c2, _, _ = am.charpoly(D)
+                    spec = am.uniaxial_split(c3, c2, qo) + (None,)
+                else:
+                    spec = am.split_spectrum(D, stats=stats, **kw)
+                    if stats is not None:
+                        stats.setdefault("n_complex", []).append(spec[4])
                 Y_in = Y
                 if stable:
                     Y, w = am.film_stable(D, Y_in, spec[:4], cfac, return_w=True)
                 else:
                     Y, w = am.film_transfer(D, Y_in, spec[:4], cfac, return_w=True)
-                if plan.fast_path:
-                    # un-tilted crystals: the kernels take the pair-symmetric closed form where it applies
-                    Yp, ok = am.film_pair_symmetric(D, Y_in, cfac)
+                if plan.fast_path or qo is not None:
+                    # un-tilted or uniaxial crystals: the kernels take the pair closed form where it applies
+                    Yp, ok = am.film_pair_uniaxial(D, Y_in, cfac, qo) if qo is not None else am.film_pair_symmetric(D, Y_in, cfac)
                     one, zero = np.ones_like(Yp[0][0]), np.zeros_like(Yp[0][0])
                     wp = ((one, zero), (zero, one))
                     if stable:
