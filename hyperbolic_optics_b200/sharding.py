@@ -105,6 +105,29 @@ def exchange_chunk(rows, ranges, index, n_chunks, rank, group=None):
     return dist.batch_isend_irecv(ops) if ops else []
 
 
+def fused_schedule(ranges, rank, n_chunks):
+    """Bookkeeping of the fused all-gather (pure function, tested on CPU): per chunk ``c`` of this
+    rank's slab ``(own, rebuild, leftover)`` -- ``own = (lo, hi)`` the points the launch computes and
+    pushes, ``rebuild`` the ranges of chunk ``c - 1`` of every peer whose Mueller matrices ride in that
+    launch (each at most ``hi - lo`` long: thread i handles element i), ``leftover`` what exceeds it
+    (epilogue launches) -- and ``tail``, the peers' last chunks, which have no later launch to ride on.
+    Every received point appears exactly once in the union of all ``rebuild``, ``leftover`` and ``tail``."""
+    others = [src for src in range(len(ranges)) if src != rank]
+    steps, pending = [], []
+    for c in range(n_chunks):
+        lo, hi = chunk_range(*ranges[rank], c, n_chunks)
+        rebuild, leftover = [], []
+        for a, b in pending:
+            m = min(b, a + max(0, hi - lo))
+            if m > a:
+                rebuild.append((a, m))
+            if b > m:
+                leftover.append((m, b))
+        steps.append(((lo, hi), rebuild, leftover))
+        pending = [r for r in (chunk_range(*ranges[src], c, n_chunks) for src in others) if r[1] > r[0]]
+    return steps, pending
+
+
 class GatheredSweep:
     """One sweep sharded over ``world_size`` GPUs, every rank ending with the WHOLE result
     (``r`` ``[4, N]`` complex128 and ``mueller`` ``[N, 4, 4]`` in presentation order).
@@ -230,22 +253,15 @@ class GatheredSweep:
             with torch.cuda.stream(compute):
                 self._hdl.barrier(channel=0)
         others = [src for src in range(self.world) if src != self.rank]
-        pending = []   # fused transport: (a, b) ranges of received r_ij whose Mueller planes are still to build
+        # Fused transport: the launch of chunk c is also the RECEIVING half for chunk c - 1 -- thread i
+        # rebuilds the Mueller matrix of element i of every range the peers pushed during the previous
+        # launch (ho_outputs_t.rebuild_*), inside the same kernel: the HBM-bound rebuild shares the
+        # SMs with the FP64-bound arithmetic instead of queueing behind it as a second kernel.
+        schedule, tail = fused_schedule(self.ranges, self.rank, self.n_chunks)
+        riding = fused and self.mueller is not None
         for c in range(self.n_chunks):
-            lo, hi = chunk_range(*self.ranges[self.rank], c, self.n_chunks)
-            # Fused transport: the launch of chunk c is also the RECEIVING half for chunk c - 1 -- thread i
-            # rebuilds the Mueller matrix of element i of every range the peers pushed during the previous
-            # launch (ho_outputs_t.rebuild_*), inside the same kernel: the HBM-bound rebuild shares the
-            # SMs with the FP64-bound arithmetic instead of queueing behind it as a second kernel.
-            rebuild, leftover = [], []
-            if fused and self.mueller is not None:
-                for a, b in pending:
-                    m = min(b, a + max(0, hi - lo))
-                    if m > a:
-                        rebuild.append((self.r[:, a:m], self.mueller[a:m]))
-                    if b > m:
-                        leftover.append((m, b))
-                pending = []
+            (lo, hi), ranges_c, leftover = schedule[c] if riding else (chunk_range(*self.ranges[self.rank], c, self.n_chunks), [], [])
+            rebuild = [(self.r[:, a:m], self.mueller[a:m]) for a, m in ranges_c]
             if hi > lo:
                 view = engine.DeviceOutputs.view(self.r[:, lo:hi], None if self.mueller is None else self.mueller[lo:hi])
                 engine.reflect(self.problem, view, lo, hi, stream=compute, peers=self._peers(lo) if fused else (), rebuild=rebuild)
@@ -255,8 +271,6 @@ class GatheredSweep:
             if fused:
                 with torch.cuda.stream(compute):
                     self._hdl.barrier(channel=1 + c % 7)     # every rank's chunk c has landed everywhere
-                if self.mueller is not None:
-                    pending = [r for r in (chunk_range(*self.ranges[src], c, self.n_chunks) for src in others) if r[1] > r[0]]
                 continue
             elif dma:
                 done = torch.cuda.Event()
@@ -287,7 +301,7 @@ class GatheredSweep:
             else:
                 compute.wait_event(arrived)
         # fused transport: the last chunk of every peer has no later launch to ride on
-        for a, b in pending:
+        for a, b in (tail if riding else []):
             polarimetry.mueller_into([self.r[i, a:b] for i in range(4)], self.mueller[a:b], stream=compute)
         if not fused:
             compute.wait_stream(self.side)

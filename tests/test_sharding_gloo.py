@@ -118,3 +118,95 @@ def test_gloo_pipelined_exchange_places_every_chunk(world, n_chunks, tmp_path):
     port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_exchange_worker, args=(world, port, "c4_fullsweep_hbn_sic", n_chunks, str(tmp_path)), nprocs=world, join=True)
     assert all(Path(tmp_path, f"rank{r}.txt").read_text() == "True" for r in range(world))
+
+
+# ---- fused all-gather: the host-side schedule, on CPU -------------------------------------------------
+@pytest.mark.parametrize("n_units,world,n_chunks", [(410, 2, 4), (410, 8, 8), (7, 3, 4), (5, 4, 2), (3, 4, 3), (64, 8, 16)])
+def test_fused_schedule_covers_every_received_point_once(n_units, world, n_chunks):
+    """sharding.fused_schedule: the Mueller rebuild of every point a rank receives is scheduled exactly
+    once -- riding in a later launch (never longer than that launch), as a leftover, or in the tail --
+    and never before the chunk it belongs to has been pushed."""
+    from hyperbolic_optics_b200 import sharding
+
+    inner = 13
+    ranges = [tuple(inner * u for u in sharding.split_units(n_units, world, r)) for r in range(world)]
+    for rank in range(world):
+        steps, tail = sharding.fused_schedule(ranges, rank, n_chunks)
+        assert len(steps) == n_chunks
+        seen = np.zeros(inner * n_units, dtype=np.int64)
+        for c, ((lo, hi), rebuild, leftover) in enumerate(steps):
+            assert (lo, hi) == sharding.chunk_range(*ranges[rank], c, n_chunks)
+            for a, b in rebuild:
+                assert 0 < b - a <= hi - lo            # thread i of the launch handles element i
+            for a, b in rebuild + leftover:
+                seen[a:b] += 1
+                # only data of the previous chunk: it landed before this launch started (barrier c - 1)
+                owners = [src for src in range(world) if ranges[src][0] <= a < ranges[src][1]]
+                assert len(owners) == 1 and owners[0] != rank
+                p_lo, p_hi = sharding.chunk_range(*ranges[owners[0]], c - 1, n_chunks)
+                assert c >= 1 and p_lo <= a and b <= p_hi
+        for a, b in tail:
+            seen[a:b] += 1
+        own = np.zeros_like(seen)
+        own[ranges[rank][0]:ranges[rank][1]] = 1
+        np.testing.assert_array_equal(seen + own, np.ones_like(seen))
+
+
+def test_gathered_sweep_enqueue_on_cpu(monkeypatch):
+    """GatheredSweep._enqueue (fused transport) with the CUDA entry points replaced by NumPy stand-ins:
+    after one step every Mueller matrix of the full result is the function of r_ij it should be, own
+    slab and received slabs alike, for an uneven 3-rank split."""
+    import torch
+
+    from hyperbolic_optics_b200 import engine, polarimetry, sharding
+    from oracle import polarimetry_port as pport
+
+    world, n_units, inner, n_chunks = 3, 7, 5, 4
+    n = n_units * inner
+    ranges = [tuple(inner * u for u in sharding.split_units(n_units, world, r)) for r in range(world)]
+    rng = np.random.default_rng(3)
+    truth_r = torch.from_numpy(rng.normal(size=(4, n)) + 1j * rng.normal(size=(4, n)))
+
+    def mueller_of(rows):
+        m = pport.mueller_from_jones(*(rows[i].numpy() for i in range(4)))
+        return torch.from_numpy(np.ascontiguousarray(m))
+
+    for rank in range(world):
+        sweep = object.__new__(sharding.GatheredSweep)
+        sweep.transport, sweep.world, sweep.rank, sweep.n_chunks, sweep.ranges, sweep.n = "fused", world, rank, n_chunks, ranges, n
+        sweep.r = torch.zeros((4, n), dtype=torch.complex128)
+        sweep.mueller = torch.full((n, 4, 4), float("nan"), dtype=torch.float64)
+        sweep.side, sweep.group = None, None
+        sweep.problem = None
+        sweep._peers = lambda lo: ()
+        landed = {"chunk": -1}
+
+        class Handle:
+            def barrier(self, channel):
+                # "every rank's chunk c has landed everywhere": the peers' chunk arrives with the barrier
+                if channel == 0:
+                    return
+                c = landed["chunk"] = landed["chunk"] + 1
+                for src in range(world):
+                    if src != rank:
+                        a, b = sharding.chunk_range(*ranges[src], c, n_chunks)
+                        sweep.r[:, a:b] = truth_r[:, a:b]
+
+        sweep._hdl = Handle()
+
+        def fake_reflect(problem, view, lo, hi, stream=None, peers=(), rebuild=()):
+            view.r[:] = truth_r[:, lo:hi]
+            view.mueller[:] = mueller_of(view.r)
+            for rows, mu in rebuild:
+                assert rows.shape[1] <= hi - lo
+                assert not torch.isnan(torch.view_as_real(rows)).any() and rows.abs().sum() > 0   # already arrived
+                mu[:] = mueller_of(rows)
+
+        def fake_mueller_into(rows, out, stream=None):
+            out[:] = mueller_of(rows)
+
+        monkeypatch.setattr(engine, "reflect", fake_reflect)
+        monkeypatch.setattr(polarimetry, "mueller_into", fake_mueller_into)
+        sweep._enqueue(None)
+        assert torch.equal(sweep.r, truth_r)
+        np.testing.assert_allclose(sweep.mueller.numpy(), mueller_of(truth_r).numpy(), rtol=0, atol=0)
