@@ -152,6 +152,60 @@ def test_descriptor_validation_without_gpu(built_library):
     assert built_library.ho_transfer_matrix(ctypes.byref(prob), None, 0, 0, None) == -1
 
 
+def test_gather_fields_validation_without_gpu(built_library):
+    """ho_outputs_t.peer_r / rebuild_* (fused all-gather) are checked on the host before any CUDA call."""
+    from hyperbolic_optics_b200 import _native as nat
+
+    kx = (ctypes.c_double * 1)(0.5)
+    one = (ctypes.c_double * 2)(1.0, 0.0)
+    prob = nat.Problem()
+    prob.A = prob.B = prob.F = prob.T = 1
+    prob.n_layers = 1
+    for name in ("kx", "k0", "prism_inv_cos", "prism_inv_ncos"):
+        setattr(prob, name, ctypes.addressof(kx))
+    prob.layers[0].kind = nat.HO_ISO_EXIT if hasattr(nat, "HO_ISO_EXIT") else 4
+    prob.layers[0].exit_cos = ctypes.addressof(one)
+    dummy = ctypes.addressof(one)
+
+    def call(out, n_end=1):
+        rc = built_library.ho_reflect(ctypes.byref(prob), ctypes.byref(out), 0, n_end, None)
+        return rc, built_library.ho_last_error()
+
+    out = nat.Outputs()
+    out.n_peers = nat.HO_MAX_PEERS + 1
+    rc, msg = call(out)
+    assert rc == -1 and b"n_peers" in msg
+    out = nat.Outputs()
+    out.n_rebuild = -1
+    rc, msg = call(out)
+    assert rc == -1 and b"n_rebuild" in msg
+    out = nat.Outputs()
+    out.n_peers = 1                                    # NULL destination
+    rc, msg = call(out)
+    assert rc == -1 and b"peer_r" in msg
+    out = nat.Outputs()
+    out.n_rebuild = 1
+    out.rebuild_n[0] = 2                               # longer than the launched range (thread i <-> element i)
+    out.rebuild_mueller[0] = dummy
+    for k in range(4):
+        out.rebuild_r[0][k] = dummy
+    rc, msg = call(out)
+    assert rc == -1 and b"rebuild_n" in msg
+    out.rebuild_n[0] = 1
+    out.rebuild_mueller[0] = None
+    rc, msg = call(out)
+    assert rc == -1 and b"rebuild_mueller" in msg
+    out.rebuild_mueller[0] = dummy
+    out.rebuild_r[0][2] = None
+    rc, msg = call(out)
+    assert rc == -1 and b"rebuild_r" in msg
+    for k in range(4):
+        out.rebuild_r[0][k] = dummy
+    out.power, out.power_stride = dummy, 1             # gather launches carry no power / transmission outputs
+    rc, msg = call(out)
+    assert rc == -1 and b"power" in msg
+
+
 def test_struct_layout_matches_header(tmp_path):
     """ctypes mirrors of the ABI structs vs what a C compiler makes of include/ho_b200.h."""
     import subprocess
