@@ -393,3 +393,42 @@ def test_structure_dies_by_reference_count():
         assert alive() is None
     finally:
         gc.enable()
+
+
+def test_install_rebinds_the_reference_structure_and_restores_it():
+    """dropin.install() / uninstall() (INTEGRATION.md route B) on the importable reference package: the
+    name `Structure` is rebound in every module that holds it -- so `compose_jones`'s isinstance test
+    and ThicknessSweep's own `Structure()` see the drop-in -- and restored afterwards.  No GPU needed:
+    nothing is executed."""
+    import importlib
+    import sys
+
+    ref_dir = ROOT / "baseline" / "_ref"
+    if not (ref_dir / "hyperbolic_optics" / "structure.py").exists():
+        pytest.skip("baseline/_ref is not populated (python tools/install_reference.py)")
+    import hyperbolic_optics_b200 as hob
+
+    sys.path.insert(0, str(ref_dir))
+    try:
+        ref_structure = importlib.import_module("hyperbolic_optics.structure")
+        original = ref_structure.Structure
+        assert original is not hob.Structure
+        patched = hob.install()
+        try:
+            assert {"hyperbolic_optics.structure", "hyperbolic_optics.mueller", "hyperbolic_optics.jones",
+                    "hyperbolic_optics.fields", "hyperbolic_optics.sweep"} <= set(patched)
+            for name in patched:
+                assert sys.modules[name].Structure is hob.Structure, name
+            assert hob.dropin.installed()
+            # the drop-in passes the reference's own type check (jones.py:404)
+            jones = importlib.import_module("hyperbolic_optics.jones")
+            assert isinstance(hob.Structure.__new__(hob.Structure), jones.Structure)
+        finally:
+            hob.uninstall()
+        for name in patched:
+            assert sys.modules[name].Structure is original, name
+        assert not hob.dropin.installed()
+    finally:
+        sys.path.remove(str(ref_dir))
+        for name in [m for m in sys.modules if m == "hyperbolic_optics" or m.startswith("hyperbolic_optics.")]:
+            del sys.modules[name]
